@@ -1,0 +1,181 @@
+"""Thin torch-side wrappers over the C ABI: raw pointers + current stream, autograd glue.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every
+forward computation on the path is a call into librbm_b200.so.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _f32c(t, name):
+    _lib.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class ParamPack:
+    """Device views of (W, a, c) plus a cached bf16 copy of W, refreshed when W changes."""
+
+    def __init__(self):
+        self._bf16 = None
+        self._key = None
+
+    def pack(self, rbm, need_bf16):
+        W = rbm.weights.detach()
+        a = rbm.visible_bias.detach()
+        c = rbm.hidden_bias.detach()
+        W = _f32c(W, "RBM weights")
+        a = _f32c(a, "RBM visible bias")
+        c = _f32c(c, "RBM hidden bias")
+        wb = None
+        if need_bf16:
+            key = (W.data_ptr(), rbm.weights._version, W.device)
+            if self._key != key or self._bf16 is None:
+                self._bf16 = W.to(torch.bfloat16)  # round-to-nearest-even
+                self._key = key
+            wb = self._bf16
+        p = _lib.RbmParams(W.shape[0], W.shape[1], W.data_ptr(), wb.data_ptr() if wb is not None else 0,
+                           a.data_ptr(), c.data_ptr())
+        return p, (W, a, c, wb)  # keep tensors alive for the duration of the call
+
+
+def half_step(rbm_pack, direction, x, mode, uniforms=None, seed=0, chain_offset=0, half_step_idx=0):
+    """out = f(x W + c) (direction 0) or f(x W^T + a) (direction 1); see rbm_b200_half_step."""
+    lib = _lib.load()
+    p, keep = rbm_pack
+    x = _f32c(x, "input state")
+    squeeze = x.dim() == 1
+    if squeeze:
+        x = x.unsqueeze(0)
+    n_in = p.n_visible if direction == 0 else p.n_hidden
+    n_out = p.n_hidden if direction == 0 else p.n_visible
+    if x.dim() != 2 or x.shape[1] != n_in:
+        raise RuntimeError("size mismatch: got input %s, RBM side has %d units" % (tuple(x.shape), n_in))
+    out = torch.empty((x.shape[0], n_out), dtype=torch.float32, device=x.device)
+    u = None
+    if mode == _lib.MODE_INJECTED:
+        u = _f32c(uniforms, "uniforms").expand(x.shape[0], n_out).contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.rbm_b200_half_step(ctypes.byref(p), direction, _ptr(x), _ptr(out), x.shape[0], mode,
+                                          _ptr(u), seed, chain_offset, half_step_idx, _stream()), "half_step")
+    return out.squeeze(0) if squeeze else out
+
+
+class _MeanFieldHalfStep(torch.autograd.Function):
+    """sigmoid(x W + c) / sigmoid(x W^T + a) with the forward in CUDA (gibbsSampler.py:20-28).
+
+    Backward is the analytic gradient of the same expression (the reference gets it
+    from autograd): g_pre = g * p (1 - p); dx = g_pre Wop^T; dW, dbias accordingly.
+    """
+
+    @staticmethod
+    def forward(ctx, x, W, bias, direction, pack):
+        out = half_step(pack, direction, x, _lib.MODE_PROBS)
+        ctx.save_for_backward(x, W, out)
+        ctx.direction = direction
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W, p = ctx.saved_tensors
+        gp = g * p * (1.0 - p)
+        x2, gp2 = (x.unsqueeze(0), gp.unsqueeze(0)) if x.dim() == 1 else (x, gp)
+        if ctx.direction == 0:
+            dx = gp2 @ W.t()
+            dW = x2.t() @ gp2
+        else:
+            dx = gp2 @ W
+            dW = gp2.t() @ x2
+        dbias = gp2.sum(0)
+        if x.dim() == 1:
+            dx = dx.squeeze(0)
+        return dx, dW, dbias, None, None
+
+
+def meanfield_half_step(rbm, pack, direction, x):
+    bias = rbm.hidden_bias if direction == 0 else rbm.visible_bias
+    return _MeanFieldHalfStep.apply(x, rbm.weights, bias, direction, pack)
+
+
+class _Energy(torch.autograd.Function):
+    """E[b] = -v.a - h.c - sum_j (vW)_j h_j, forward in CUDA (models/rbm/rbm.py:56-72)."""
+
+    @staticmethod
+    def forward(ctx, v, h, W, a, c, pack):
+        lib = _lib.load()
+        p, keep = pack
+        v = _f32c(v, "energy input"); h = _f32c(h, "energy input")
+        B = v.shape[0]
+        E = torch.empty(B, dtype=torch.float32, device=v.device)
+        nbytes = lib.rbm_b200_energy_workspace(p.n_visible, p.n_hidden, B)
+        ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=v.device)
+        with torch.cuda.device(v.device):
+            _lib.check(lib.rbm_b200_energy(ctypes.byref(p), _ptr(v), _ptr(h), _ptr(E), B, _ptr(ws), nbytes,
+                                           _stream()), "energy")
+        ctx.save_for_backward(v, h, W, a, c)
+        return E
+
+    @staticmethod
+    def backward(ctx, g):
+        v, h, W, a, c = ctx.saved_tensors
+        gv = -(g[:, None] * (a[None, :] + h @ W.t()))
+        gh = -(g[:, None] * (c[None, :] + v @ W))
+        gW = -(v * g[:, None]).t() @ h
+        ga = -(v * g[:, None]).sum(0)
+        gc = -(h * g[:, None]).sum(0)
+        return gv, gh, gW, ga, gc, None
+
+
+def energy(rbm, pack, v, h):
+    return _Energy.apply(v, h, rbm.weights, rbm.visible_bias, rbm.hidden_bias, pack)
+
+
+def negative_phase_stats(v, h, scale=None):
+    """(S_vh, S_v, S_h) = scale * (V^T H, sum V, sum H); scale defaults to 1/B (means)."""
+    lib = _lib.load()
+    v = _f32c(v, "visible states"); h = _f32c(h, "hidden states")
+    B, nV = v.shape
+    nH = h.shape[1]
+    if scale is None:
+        scale = 1.0 / max(B, 1)
+    S = torch.empty((nV, nH), dtype=torch.float32, device=v.device)
+    sv = torch.empty(nV, dtype=torch.float32, device=v.device)
+    sh = torch.empty(nH, dtype=torch.float32, device=v.device)
+    with torch.cuda.device(v.device):
+        _lib.check(lib.rbm_b200_negative_phase(_ptr(v), _ptr(h), B, nV, nH, scale, _ptr(S), _ptr(sv), _ptr(sh),
+                                               _stream()), "negative_phase")
+    return S, sv, sh
+
+
+class _EnergyExpFromStats(torch.autograd.Function):
+    """mean_b E(v_b, h_b) = -(<W, S_vh> + a.S_v + c.S_h) with gradients -S_vh, -S_v, -S_h.
+
+    Replaces GumBolt.energy_exp on detached PCD samples (gumbolt.py:102-134): same value,
+    same autograd result, without the [B, nV, nH] broadcast.
+    """
+
+    @staticmethod
+    def forward(ctx, W, a, c, S, sv, sh):
+        ctx.save_for_backward(S, sv, sh)
+        return -((W * S).sum() + (a * sv).sum() + (c * sh).sum())
+
+    @staticmethod
+    def backward(ctx, g):
+        S, sv, sh = ctx.saved_tensors
+        return -g * S, -g * sv, -g * sh, None, None, None
+
+
+def energy_exp_from_stats(rbm, S, sv, sh):
+    return _EnergyExpFromStats.apply(rbm.weights, rbm.visible_bias, rbm.hidden_bias, S, sv, sh)

@@ -1,0 +1,207 @@
+// extern "C" entry points of librbm_b200.so (include/rbm_b200.h) and variant dispatch.
+#include <cstring>
+
+#include "common.cuh"
+#include "philox.cuh"
+#include "variants.h"
+
+namespace rbm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+
+static int check_params(const rbm_b200_params* p, bool need_f32) {
+  RBM_REQUIRE(p != nullptr, RBM_B200_ERR_INVALID, "params is NULL");
+  RBM_REQUIRE(p->n_visible > 0 && p->n_hidden > 0, RBM_B200_ERR_INVALID, "bad RBM shape %d x %d",
+              p->n_visible, p->n_hidden);
+  RBM_REQUIRE(p->vbias && p->hbias, RBM_B200_ERR_INVALID, "bias pointer is NULL");
+  if (need_f32) RBM_REQUIRE(p->W != nullptr, RBM_B200_ERR_INVALID, "fp32 W is required by this entry");
+  return 0;
+}
+
+static int require_device() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s): librbm_b200 has no CPU fallback", cudaGetErrorString(e));
+    return RBM_B200_ERR_NO_DEVICE;
+  }
+  return 0;
+}
+
+int pick_variant(const rbm_b200_params* p, int64_t B, int variant) {
+  if (variant != RBM_B200_VARIANT_AUTO) return variant;
+  if (p->W_bf16 && smem_variant_supported(p->n_visible, p->n_hidden)) return RBM_B200_VARIANT_SMEM;
+  if (p->W_bf16 && umma_variant_supported(p->n_visible, p->n_hidden) && B >= 128) return RBM_B200_VARIANT_UMMA;
+  return RBM_B200_VARIANT_GENERAL;
+}
+
+}  // namespace rbm
+
+using namespace rbm;
+
+extern "C" {
+
+int rbm_b200_abi_version(void) { return RBM_B200_ABI_VERSION; }
+
+const char* rbm_b200_last_error(void) { return g_err; }
+
+int rbm_b200_device_info(int32_t* sm_count, int32_t* smem_optin, int32_t* cc) {
+  int rc = require_device();
+  if (rc) return rc;
+  int dev = 0, v = 0, maj = 0, min = 0;
+  RBM_CUDA_TRY(cudaGetDevice(&dev));
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+  if (sm_count) *sm_count = v;
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem_optin) *smem_optin = v;
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  if (cc) *cc = maj * 10 + min;
+  return 0;
+}
+
+int rbm_b200_half_step(const rbm_b200_params* p, int direction, const float* in, float* out, int64_t B,
+                       int mode, const float* uniforms, uint64_t seed, uint64_t chain_offset,
+                       uint64_t half_step, void* stream) {
+  int rc = check_params(p, true);
+  if (rc) return rc;
+  RBM_REQUIRE(direction == 0 || direction == 1, RBM_B200_ERR_INVALID, "direction must be 0 or 1");
+  RBM_REQUIRE(B >= 0, RBM_B200_ERR_INVALID, "negative batch");
+  RBM_REQUIRE(B == 0 || (in && out), RBM_B200_ERR_INVALID, "in/out is NULL");
+  RBM_REQUIRE(mode != RBM_B200_MODE_INJECTED || uniforms || B == 0, RBM_B200_ERR_INVALID,
+              "injected mode needs uniforms");
+  if ((rc = require_device())) return rc;
+  return general_half_step(p, direction, in, out, B, mode, uniforms, seed, chain_offset, half_step,
+                           TAG_GIBBS, (cudaStream_t)stream);
+}
+
+int rbm_b200_init_chains(float* v, int64_t B, int32_t n_visible, uint64_t seed, uint64_t chain_offset,
+                         uint64_t step_offset, void* stream) {
+  RBM_REQUIRE(B >= 0 && n_visible > 0, RBM_B200_ERR_INVALID, "bad shape");
+  RBM_REQUIRE(B == 0 || v, RBM_B200_ERR_INVALID, "v is NULL");
+  int rc = require_device();
+  if (rc) return rc;
+  return general_init_chains(v, B, n_visible, seed, chain_offset, step_offset, (cudaStream_t)stream);
+}
+
+size_t rbm_b200_block_gibbs_workspace(int32_t n_visible, int32_t n_hidden, int64_t B, int variant) {
+  if (B <= 0) return 0;
+  rbm_b200_params q{};
+  q.n_visible = n_visible; q.n_hidden = n_hidden; q.W_bf16 = (const uint16_t*)1;
+  switch (pick_variant(&q, B, variant)) {
+    case RBM_B200_VARIANT_UMMA: return umma_workspace_bytes(n_visible, n_hidden, B);
+    case RBM_B200_VARIANT_SMEM: return smem_workspace_bytes(n_visible, n_hidden, B);
+    default: return 0;
+  }
+}
+
+int rbm_b200_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int32_t k,
+                         int init_chains, uint64_t seed, uint64_t chain_offset, uint64_t step_offset,
+                         int variant, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_params(p, false);
+  if (rc) return rc;
+  RBM_REQUIRE(B >= 0 && k >= 0, RBM_B200_ERR_INVALID, "negative batch or step count");
+  RBM_REQUIRE(B == 0 || (v && h), RBM_B200_ERR_INVALID, "state pointer is NULL");
+  RBM_REQUIRE(variant >= RBM_B200_VARIANT_AUTO && variant <= RBM_B200_VARIANT_UMMA, RBM_B200_ERR_INVALID,
+              "unknown variant %d", variant);
+  if ((rc = require_device())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return 0;
+  const int chosen = pick_variant(p, B, variant);
+  if (chosen == RBM_B200_VARIANT_SMEM) {
+    RBM_REQUIRE(p->W_bf16, RBM_B200_ERR_INVALID, "SMEM variant needs W_bf16");
+    return smem_block_gibbs(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, workspace,
+                            workspace_bytes, st);
+  }
+  if (chosen == RBM_B200_VARIANT_UMMA) {
+    RBM_REQUIRE(p->W_bf16, RBM_B200_ERR_INVALID, "UMMA variant needs W_bf16");
+    return umma_block_gibbs(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, workspace,
+                            workspace_bytes, st);
+  }
+  RBM_REQUIRE(p->W, RBM_B200_ERR_INVALID, "GENERAL variant needs fp32 W");
+  if (init_chains) {
+    if ((rc = general_init_chains(v, B, p->n_visible, seed, chain_offset, step_offset, st))) return rc;
+  }
+  for (int s = 0; s < k; ++s) {
+    if ((rc = general_half_step(p, 0, v, h, B, RBM_B200_MODE_SAMPLE, nullptr, seed, chain_offset,
+                                step_offset + 2ull * s, TAG_GIBBS, st))) return rc;
+    if ((rc = general_half_step(p, 1, h, v, B, RBM_B200_MODE_SAMPLE, nullptr, seed, chain_offset,
+                                step_offset + 2ull * s + 1, TAG_GIBBS, st))) return rc;
+  }
+  return 0;
+}
+
+int rbm_b200_block_gibbs_injected(const rbm_b200_params* p, float* v, float* h, int64_t B, int32_t k,
+                                  const float* uniforms_h, const float* uniforms_v, void* stream) {
+  int rc = check_params(p, true);
+  if (rc) return rc;
+  RBM_REQUIRE(B >= 0 && k >= 0, RBM_B200_ERR_INVALID, "negative batch or step count");
+  RBM_REQUIRE(B == 0 || k == 0 || (v && h && uniforms_h && uniforms_v), RBM_B200_ERR_INVALID, "NULL pointer");
+  if ((rc = require_device())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int s = 0; s < k; ++s) {
+    if ((rc = general_half_step(p, 0, v, h, B, RBM_B200_MODE_INJECTED,
+                                uniforms_h + (size_t)s * B * p->n_hidden, 0, 0, 0, TAG_GIBBS, st))) return rc;
+    if ((rc = general_half_step(p, 1, h, v, B, RBM_B200_MODE_INJECTED,
+                                uniforms_v + (size_t)s * B * p->n_visible, 0, 0, 0, TAG_GIBBS, st))) return rc;
+  }
+  return 0;
+}
+
+int rbm_b200_meanfield(const rbm_b200_params* p, float* left, float* right, int64_t B, int32_t k,
+                       void* stream) {
+  int rc = check_params(p, true);
+  if (rc) return rc;
+  RBM_REQUIRE(B >= 0 && k >= 0, RBM_B200_ERR_INVALID, "negative batch or step count");
+  RBM_REQUIRE(B == 0 || (left && right), RBM_B200_ERR_INVALID, "NULL pointer");
+  if ((rc = require_device())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int s = 0; s < k; ++s) {
+    if ((rc = general_half_step(p, 0, left, right, B, RBM_B200_MODE_PROBS, nullptr, 0, 0, 0, TAG_GIBBS, st))) return rc;
+    if ((rc = general_half_step(p, 1, right, left, B, RBM_B200_MODE_PROBS, nullptr, 0, 0, 0, TAG_GIBBS, st))) return rc;
+  }
+  return 0;
+}
+
+size_t rbm_b200_energy_workspace(int32_t n_visible, int32_t n_hidden, int64_t B) {
+  (void)n_visible;
+  if (B <= 0 || n_hidden <= 0) return 0;
+  return sizeof(float) * (size_t)B * (size_t)ceil_div(n_hidden, 64);
+}
+
+int rbm_b200_energy(const rbm_b200_params* p, const float* v, const float* h, float* E, int64_t B,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_params(p, true);
+  if (rc) return rc;
+  RBM_REQUIRE(B >= 0, RBM_B200_ERR_INVALID, "negative batch");
+  if (B == 0) return 0;
+  RBM_REQUIRE(v && h && E, RBM_B200_ERR_INVALID, "NULL pointer");
+  RBM_REQUIRE(workspace && workspace_bytes >= rbm_b200_energy_workspace(p->n_visible, p->n_hidden, B),
+              RBM_B200_ERR_WORKSPACE, "energy workspace too small");
+  if ((rc = require_device())) return rc;
+  return general_energy(p, v, h, E, B, (float*)workspace, (cudaStream_t)stream);
+}
+
+int rbm_b200_negative_phase(const float* v, const float* h, int64_t B, int32_t n_visible, int32_t n_hidden,
+                            float scale, float* S_vh, float* S_v, float* S_h, void* stream) {
+  RBM_REQUIRE(B >= 0 && n_visible > 0 && n_hidden > 0, RBM_B200_ERR_INVALID, "bad shape");
+  RBM_REQUIRE(S_vh && S_v && S_h && (B == 0 || (v && h)), RBM_B200_ERR_INVALID, "NULL pointer");
+  int rc = require_device();
+  if (rc) return rc;
+  return general_negative_phase(v, h, B, n_visible, n_hidden, scale, S_vh, S_v, S_h, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// Shared host/device helpers: error handling, thread-local error string, launch checks.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/rbm_b200.h"
+
+namespace rbm {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define RBM_CUDA_TRY(expr)                                         \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return ::rbm::cuda_fail(_e, #expr);     \
+  } while (0)
+
+#define RBM_REQUIRE(cond, code, ...)                               \
+  do {                                                             \
+    if (!(cond)) { ::rbm::set_error(__VA_ARGS__); return (code); } \
+  } while (0)
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return cuda_fail(cudaGetLastError(), what);
+  return 0;
+}
+
+__host__ __device__ constexpr int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+}  // namespace rbm

@@ -1,0 +1,326 @@
+// General fp32 SIMT kernels: any shape, fp32 W, one launch per half-step.
+//
+// These are the exact-fp32 restatement of the reference's per-half-step op chain
+//   matmul -> +bias -> sigmoid -> rand -> >= -> float   (models/samplers/pcd.py:32-35,46-49)
+// fused into one kernel, plus the mean-field variant without the draw
+// (models/samplers/gibbsSampler.py:20-28), the per-sample energy (models/rbm/rbm.py:56-72)
+// and the negative-phase statistics (models/autoencoders/gumbolt.py:109-134 via autograd).
+// They serve odd shapes (200x200, 784x128), real-valued inputs, injected uniforms and
+// small batches; the SMEM and UMMA variants are the fast paths for binary chains.
+#include <algorithm>
+
+#include "common.cuh"
+#include "philox.cuh"
+#include "variants.h"
+
+namespace rbm {
+
+constexpr int GBM = 64, GBN = 64, GBK = 16;  // CTA tile: 64 rows x 64 units, 256 threads, 4x4 per thread
+
+// acc[i][j] = sum_k in[row0 + ty*4 + i][k] * Wop[k][n0 + tx*4 + j]
+// TRANS = false: Wop[k][n] = W[k*ldw + n]   (v -> h, K = nV, N = nH)
+// TRANS = true : Wop[k][n] = W[n*ldw + k]   (h -> v, K = nH, N = nV)
+template <bool TRANS>
+__device__ __forceinline__ void sgemm_tile(const float* __restrict__ in, const float* __restrict__ W,
+                                           int64_t B, int K, int N, int ldw, int64_t row0, int n0,
+                                           float (&acc)[4][4]) {
+  __shared__ float As[GBK][GBM + 4];
+  __shared__ float Bs[GBK][GBN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += GBK) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      int idx = tid + l * 256;
+      int r = idx >> 4, kk = idx & 15;
+      int64_t row = row0 + r;
+      int k = k0 + kk;
+      As[kk][r] = (row < B && k < K) ? in[row * (int64_t)K + k] : 0.f;
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      int idx = tid + l * 256;
+      if (!TRANS) {
+        int kk = idx >> 6, n = idx & 63;
+        int k = k0 + kk, col = n0 + n;
+        Bs[kk][n] = (k < K && col < N) ? W[(int64_t)k * ldw + col] : 0.f;
+      } else {
+        int n = idx >> 4, kk = idx & 15;
+        int k = k0 + kk, col = n0 + n;
+        Bs[kk][n] = (k < K && col < N) ? W[(int64_t)col * ldw + k] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GBK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+
+template <bool TRANS, int MODE>
+__global__ void __launch_bounds__(256)
+half_step_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                 const float* __restrict__ bias, float* __restrict__ out,
+                 const float* __restrict__ U, int64_t B, int K, int N, int ldw,
+                 DrawCtx ctx, uint64_t chain_offset) {
+  const int64_t row0 = (int64_t)blockIdx.x * GBM;
+  const int n0 = blockIdx.y * GBN;
+  float acc[4][4];
+  sgemm_tile<TRANS>(in, W, B, K, N, ldw, row0, n0, acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = row0 + ty * 4 + i;
+    if (row >= B) continue;
+    const uint32_t chain = (uint32_t)(chain_offset + (uint64_t)row);
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {  // column pairs share one Philox block
+      const int col = n0 + tx * 4 + jp * 2;
+      if (col >= N) continue;
+      uint4 w = make_uint4(0, 0, 0, 0);
+      if (MODE == RBM_B200_MODE_SAMPLE) w = draw_block(ctx, unit_block_of(col), chain);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = col + e;
+        if (c >= N) continue;
+        const float x = acc[i][jp * 2 + e] + bias[c];
+        float r;
+        if (MODE == RBM_B200_MODE_PROBS) {
+          r = sigmoid_precise(x);
+        } else if (MODE == RBM_B200_MODE_INJECTED) {
+          r = (sigmoid_precise(x) >= U[row * (int64_t)N + c]) ? 1.f : 0.f;
+        } else {
+          const uint32_t slot = unit_slot_of(c);
+          const uint32_t blk = unit_block_of(c);
+          r = bernoulli_from_preact(x, field16(w, slot), [&]() {
+                return field16(draw_block_extra(ctx, blk, chain), slot);
+              }) ? 1.f : 0.f;
+        }
+        out[row * (int64_t)N + c] = r;
+      }
+    }
+  }
+}
+
+__global__ void init_chains_kernel(float* __restrict__ v, int64_t B, int nV, DrawCtx ctx,
+                                   uint64_t chain_offset) {
+  // one thread per (chain, unit_block): eight units per Philox call
+  const int nblk = ceil_div(nV, 32) * 4;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * nblk) return;
+  const int64_t row = idx / nblk;
+  const int blk = (int)(idx % nblk);
+  const uint4 w = draw_block(ctx, (uint32_t)blk, (uint32_t)(chain_offset + (uint64_t)row));
+  const int base = (blk >> 2) * 32 + (blk & 3) * 2;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int c = base + (s >> 1) * 8 + (s & 1);
+    if (c < nV) v[row * (int64_t)nV + c] = (field16(w, s) >> 15) ? 0.f : 1.f;
+  }
+}
+
+// ---- energy: E[b] = -(v.a + h.c + sum_j (vW)_j h_j), deterministic two-pass reduction -------------
+__global__ void __launch_bounds__(256)
+energy_partial_kernel(const float* __restrict__ v, const float* __restrict__ h,
+                      const float* __restrict__ W, float* __restrict__ part, int64_t B, int nV,
+                      int nH, int nparts) {
+  const int64_t row0 = (int64_t)blockIdx.x * GBM;
+  const int n0 = blockIdx.y * GBN;
+  float acc[4][4];
+  sgemm_tile<false>(v, W, B, nV, nH, nH, row0, n0, acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = row0 + ty * 4 + i;
+    float s = 0.f;
+    if (row < B) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = n0 + tx * 4 + j;
+        if (c < nH) s = fmaf(acc[i][j], h[row * (int64_t)nH + c], s);
+      }
+    }
+    // fixed-order tree over the 16 tx lanes (a half-warp)
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, 16);
+    if (tx == 0 && row < B) part[row * (int64_t)nparts + blockIdx.y] = s;
+  }
+}
+
+__global__ void energy_finalize_kernel(const float* __restrict__ v, const float* __restrict__ h,
+                                       const float* __restrict__ a, const float* __restrict__ c,
+                                       const float* __restrict__ part, float* __restrict__ E,
+                                       int64_t B, int nV, int nH, int nparts) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float s = 0.f;
+  for (int i = lane; i < nV; i += 32) s = fmaf(v[row * (int64_t)nV + i], a[i], s);
+  for (int j = lane; j < nH; j += 32) s = fmaf(h[row * (int64_t)nH + j], c[j], s);
+  for (int q = lane; q < nparts; q += 32) s += part[row * (int64_t)nparts + q];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) E[row] = -s;
+}
+
+// ---- negative-phase statistics: S_vh = scale * V^T H, S_v, S_h -----------------------------------
+// 64x64 output tile per CTA, split over the chain dimension (gridDim.z); partial sums are
+// accumulated with atomicAdd.  For binary states the partials are integers < 2^24, so the
+// result is exact and independent of the accumulation order.
+__global__ void __launch_bounds__(256)
+stats_kernel(const float* __restrict__ v, const float* __restrict__ h, int64_t B, int nV, int nH,
+             int64_t rows_per_split, float* __restrict__ S) {
+  __shared__ float Vs[GBK][GBM + 4];
+  __shared__ float Hs[GBK][GBN + 4];
+  const int i0 = blockIdx.x * GBM, j0 = blockIdx.y * GBN;
+  const int64_t b_begin = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t b_end = min(B, b_begin + rows_per_split);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4] = {};
+  for (int64_t b0 = b_begin; b0 < b_end; b0 += GBK) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      int idx = tid + l * 256;
+      int kk = idx >> 6, n = idx & 63;
+      int64_t b = b0 + kk;
+      Vs[kk][n] = (b < b_end && i0 + n < nV) ? v[b * (int64_t)nV + i0 + n] : 0.f;
+      Hs[kk][n] = (b < b_end && j0 + n < nH) ? h[b * (int64_t)nH + j0 + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GBK; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Vs[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Hs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = i0 + ty * 4 + i, c = j0 + tx * 4 + j;
+      if (r < nV && c < nH) atomicAdd(&S[(int64_t)r * nH + c], acc[i][j]);
+    }
+}
+
+// column sums: out[c] = sum_b x[b][c]; grid (ceil(n/256), splits)
+__global__ void colsum_kernel(const float* __restrict__ x, int64_t B, int n, int64_t rows_per_split,
+                              float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int64_t b_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t b_end = min(B, b_begin + rows_per_split);
+  float s = 0.f;
+  for (int64_t b = b_begin; b < b_end; ++b) s += x[b * (int64_t)n + c];
+  atomicAdd(&out[c], s);
+}
+
+__global__ void scale_kernel(float* __restrict__ x, int64_t n, float scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= scale;
+}
+
+// ------------------------------------------------------------------------------- host launchers
+template <int MODE>
+static int launch_half_step(const rbm_b200_params* p, int direction, const float* in, float* out,
+                            int64_t B, const float* U, DrawCtx ctx, uint64_t chain_offset,
+                            cudaStream_t st) {
+  const int K = direction == 0 ? p->n_visible : p->n_hidden;
+  const int N = direction == 0 ? p->n_hidden : p->n_visible;
+  const float* bias = direction == 0 ? p->hbias : p->vbias;
+  dim3 grid((unsigned)ceil_div64(B, GBM), (unsigned)ceil_div(N, GBN));
+  if (direction == 0)
+    half_step_kernel<false, MODE><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset);
+  else
+    half_step_kernel<true, MODE><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset);
+  return check_launch("half_step_kernel");
+}
+
+int general_half_step(const rbm_b200_params* p, int direction, const float* in, float* out, int64_t B,
+                      int mode, const float* U, uint64_t seed, uint64_t chain_offset,
+                      uint64_t half_step, uint32_t tag, cudaStream_t st) {
+  if (B == 0) return 0;
+  DrawCtx ctx = make_draw_ctx(seed, half_step, tag);
+  switch (mode) {
+    case RBM_B200_MODE_SAMPLE: return launch_half_step<RBM_B200_MODE_SAMPLE>(p, direction, in, out, B, U, ctx, chain_offset, st);
+    case RBM_B200_MODE_INJECTED: return launch_half_step<RBM_B200_MODE_INJECTED>(p, direction, in, out, B, U, ctx, chain_offset, st);
+    case RBM_B200_MODE_PROBS: return launch_half_step<RBM_B200_MODE_PROBS>(p, direction, in, out, B, U, ctx, chain_offset, st);
+  }
+  set_error("unknown half-step mode %d", mode);
+  return RBM_B200_ERR_INVALID;
+}
+
+int general_init_chains(float* v, int64_t B, int nV, uint64_t seed, uint64_t chain_offset,
+                        uint64_t step_offset, cudaStream_t st) {
+  if (B == 0) return 0;
+  const int nblk = ceil_div(nV, 32) * 4;
+  const int64_t total = B * nblk;
+  init_chains_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(
+      v, B, nV, make_draw_ctx(seed, step_offset, TAG_INIT), chain_offset);
+  return check_launch("init_chains_kernel");
+}
+
+int general_energy(const rbm_b200_params* p, const float* v, const float* h, float* E, int64_t B,
+                   float* part, cudaStream_t st) {
+  if (B == 0) return 0;
+  const int nparts = ceil_div(p->n_hidden, GBN);
+  dim3 grid((unsigned)ceil_div64(B, GBM), (unsigned)nparts);
+  energy_partial_kernel<<<grid, 256, 0, st>>>(v, h, p->W, part, B, p->n_visible, p->n_hidden, nparts);
+  int rc = check_launch("energy_partial_kernel");
+  if (rc) return rc;
+  energy_finalize_kernel<<<(unsigned)ceil_div64(B, 8), 256, 0, st>>>(v, h, p->vbias, p->hbias, part, E, B,
+                                                                     p->n_visible, p->n_hidden, nparts);
+  return check_launch("energy_finalize_kernel");
+}
+
+int general_negative_phase(const float* v, const float* h, int64_t B, int nV, int nH, float scale,
+                           float* S_vh, float* S_v, float* S_h, cudaStream_t st) {
+  RBM_CUDA_TRY(cudaMemsetAsync(S_vh, 0, sizeof(float) * (size_t)nV * nH, st));
+  RBM_CUDA_TRY(cudaMemsetAsync(S_v, 0, sizeof(float) * (size_t)nV, st));
+  RBM_CUDA_TRY(cudaMemsetAsync(S_h, 0, sizeof(float) * (size_t)nH, st));
+  if (B == 0) return 0;
+  const int tiles = ceil_div(nV, GBM) * ceil_div(nH, GBN);
+  int splits = (int)std::min<int64_t>(ceil_div64(B, 256), std::max(1, 592 / tiles));
+  int64_t rows_per_split = ceil_div64(ceil_div64(B, splits), GBK) * GBK;
+  splits = (int)ceil_div64(B, rows_per_split);
+  dim3 grid((unsigned)ceil_div(nV, GBM), (unsigned)ceil_div(nH, GBN), (unsigned)splits);
+  stats_kernel<<<grid, 256, 0, st>>>(v, h, B, nV, nH, rows_per_split, S_vh);
+  int rc = check_launch("stats_kernel");
+  if (rc) return rc;
+  int csplits = (int)std::min<int64_t>(ceil_div64(B, 64), 64);
+  int64_t crows = ceil_div64(B, csplits);
+  csplits = (int)ceil_div64(B, crows);
+  colsum_kernel<<<dim3((unsigned)ceil_div(nV, 256), (unsigned)csplits), 256, 0, st>>>(v, B, nV, crows, S_v);
+  colsum_kernel<<<dim3((unsigned)ceil_div(nH, 256), (unsigned)csplits), 256, 0, st>>>(h, B, nH, crows, S_h);
+  rc = check_launch("colsum_kernel");
+  if (rc) return rc;
+  // raw sums are exact integers for binary states; scale once at the end
+  scale_kernel<<<(unsigned)ceil_div64((int64_t)nV * nH, 256), 256, 0, st>>>(S_vh, (int64_t)nV * nH, scale);
+  scale_kernel<<<(unsigned)ceil_div(nV, 256), 256, 0, st>>>(S_v, nV, scale);
+  scale_kernel<<<(unsigned)ceil_div(nH, 256), 256, 0, st>>>(S_h, nH, scale);
+  return check_launch("scale_kernel");
+}
+
+}  // namespace rbm

@@ -1,0 +1,36 @@
+// Internal interface between the C ABI (abi.cu) and the kernel variants.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/rbm_b200.h"
+
+namespace rbm {
+
+// gibbs_general.cu
+int general_half_step(const rbm_b200_params* p, int direction, const float* in, float* out, int64_t B,
+                      int mode, const float* U, uint64_t seed, uint64_t chain_offset,
+                      uint64_t half_step, uint32_t tag, cudaStream_t st);
+int general_init_chains(float* v, int64_t B, int nV, uint64_t seed, uint64_t chain_offset,
+                        uint64_t step_offset, cudaStream_t st);
+int general_energy(const rbm_b200_params* p, const float* v, const float* h, float* E, int64_t B,
+                   float* part, cudaStream_t st);
+int general_negative_phase(const float* v, const float* h, int64_t B, int nV, int nH, float scale,
+                           float* S_vh, float* S_v, float* S_h, cudaStream_t st);
+
+// gibbs_smem.cu — persistent kernel, W (bf16) resident in shared memory
+bool smem_variant_supported(int nV, int nH);
+size_t smem_workspace_bytes(int nV, int nH, int64_t B);
+int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains,
+                     uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws,
+                     size_t ws_bytes, cudaStream_t st);
+
+// gibbs_umma.cu — tcgen05/TMEM GEMM per half-step fed by TMA
+bool umma_variant_supported(int nV, int nH);
+size_t umma_workspace_bytes(int nV, int nH, int64_t B);
+int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains,
+                     uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws,
+                     size_t ws_bytes, cudaStream_t st);
+
+}  // namespace rbm

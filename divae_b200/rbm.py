@@ -1,0 +1,80 @@
+"""RBM prior — same API as the reference's models/rbm/rbm.py:14-80, CUDA arithmetic.
+
+Parameters keep the reference's names (`_weights`, `_visible_bias`, `_hidden_bias`),
+shapes, dtype (fp32 nn.Parameter, requires_grad) and initialisation (rbm.py:28-34), so
+optimisers and state_dict keys are unchanged (SURVEY.md §5 checkpoint).
+"""
+import logging
+
+import torch
+from torch import nn
+
+from . import _ops
+
+logger = logging.getLogger(__name__)
+
+
+class RBM(nn.Module):
+    def __init__(self, n_visible, n_hidden, **kwargs):
+        super(RBM, self).__init__(**kwargs)
+        self._n_visible = n_visible
+        self._n_hidden = n_hidden
+        require_grad = True
+        # rbm.py:28 — weights ~ N(0, 0.01^2); rbm.py:32 — visible bias 0.5; rbm.py:34 — hidden bias 0
+        self._weights = nn.Parameter(torch.randn(n_visible, n_hidden) * 0.01, requires_grad=require_grad)
+        self._visible_bias = nn.Parameter(torch.ones(n_visible) * 0.5, requires_grad=require_grad)
+        self._hidden_bias = nn.Parameter(torch.zeros(n_hidden), requires_grad=require_grad)
+        self._logZ = None          # set by estimate_logZ(); None -> the reference's placeholder
+        self._pack = _ops.ParamPack()
+
+    # rbm.py:36-46
+    @property
+    def visible_bias(self):
+        return self._visible_bias
+
+    @property
+    def hidden_bias(self):
+        return self._hidden_bias
+
+    @property
+    def weights(self):
+        return self._weights
+
+    # legacy getters used by the reference's dead code (contrastiveDivergence.py:35-37)
+    def get_weights(self):
+        return self._weights
+
+    def get_visible_bias(self):
+        return self._visible_bias
+
+    def get_hidden_bias(self):
+        return self._hidden_bias
+
+    def __repr__(self):
+        return "RBM: n_vis={0}, n_hid={1}".format(self._n_visible, self._n_hidden)
+
+    def get_logZ_value(self):
+        """rbm.py:51-54 returns the literal 33.65; an AIS estimate replaces it once computed."""
+        if self._logZ is not None:
+            return self._logZ
+        return 33.65
+
+    def energy(self, post_samples):
+        """Energy of samples, vis*b_vis + hid*b_hid + vis*w*hid (rbm.py:56-72).
+
+        `post_samples` is a list of [B, *] tensors, concatenated and split in halves
+        exactly like the reference.  Differentiable w.r.t. samples and parameters.
+        """
+        post_samples_concat = torch.cat(post_samples, dim=1)
+        n_split = post_samples_concat.size()[1] // 2
+        v, h = torch.split(post_samples_concat, split_size_or_sections=int(n_split), dim=1)[:2]
+        pack = self._pack.pack(self, need_bf16=False)
+        return _ops.energy(self, pack, v, h)
+
+    def cross_entropy(self, post_samples):
+        """rbm.py:74-76."""
+        return -self.log_prob(post_samples)
+
+    def log_prob(self, samples):
+        """log(exp(-E(z))/Z) = -E(z) - log(Z) (rbm.py:78-80)."""
+        return -self.energy(samples) - self.get_logZ_value()

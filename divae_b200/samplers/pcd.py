@@ -1,0 +1,140 @@
+"""PCD block-Gibbs sampler — mirrors models/samplers/pcd.py:10-69 on top of librbm_b200.so.
+
+Reference behaviour kept:
+  * `PCD(batch_size, RBM, n_gibbs_sampling_steps)`; `get_batch_size()`;
+    `hidden_samples(v)`, `visible_samples(h)` draw `(sigmoid(.) >= u).float()`;
+  * `block_gibbs_sampling()` returns `(v, h)` float32 {0,1} on the parameters' device,
+    h drawn from the previous v and v from that h (pcd.py:60-62,69);
+  * the chain state is NOT persistent: every call starts from a fresh Bernoulli(1/2)
+    state (pcd.py:64-67) — drawn on the device here instead of CPU RNG + H2D copy;
+  * `_RBM` is a registered submodule (duplicate `sampler._RBM.*` state_dict keys),
+    `_MCState` is a plain attribute (not a buffer, not checkpointed).
+Additive, defaults preserve the reference: `persistent`, `seed`, `variant`,
+`chain_offset` (global id of this shard's first chain), `negative_phase()`.
+The k-step loop is ONE library call: a persistent shared-memory kernel for small priors,
+tcgen05 GEMM half-steps for large ones (BASELINE.json north_star).
+"""
+import ctypes
+
+import torch
+
+from .. import _lib, _ops
+from .baseSampler import BaseSampler
+
+
+class PCD(BaseSampler):
+
+    def __init__(self, batch_size, RBM, persistent=False, seed=None, variant="auto", chain_offset=0,
+                 **kwargs):
+        super(PCD, self).__init__(**kwargs)
+        self._RBM = RBM
+        self._batch_size = batch_size
+        # pcd.py:16-17 draws the first state with CPU RNG; here the state is drawn on the
+        # device at call time, so nothing is materialised until the first call.
+        self._MCState = None
+        self._persistent = bool(persistent)
+        if seed is None:
+            # tie the Philox key to torch's global generator so torch.manual_seed()
+            # (scripts/run.py:17) still makes runs reproducible
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        if variant not in _lib.VARIANTS:
+            raise ValueError("variant must be one of %s" % sorted(_lib.VARIANTS))
+        self._variant = _lib.VARIANTS[variant]
+        self._chain_offset = int(chain_offset)
+        self._half_steps = 0  # draw counter: advances by 2k per call
+        self._pack = _ops.ParamPack()
+        self._workspace = None
+
+    def get_batch_size(self):
+        return self._batch_size
+
+    # --------------------------------------------------------------- single half-steps
+    def _next_half_step(self):
+        t = self._half_steps
+        self._half_steps += 1
+        return t
+
+    def hidden_samples(self, visible_states):
+        """h ~ Bernoulli(sigmoid(v W + c)) (pcd.py:23-35)."""
+        pack = self._pack.pack(self._RBM, need_bf16=False)
+        with torch.no_grad():
+            return _ops.half_step(pack, 0, visible_states, _lib.MODE_SAMPLE, seed=self._seed,
+                                  chain_offset=self._chain_offset, half_step_idx=self._next_half_step())
+
+    def visible_samples(self, hidden_states):
+        """v ~ Bernoulli(sigmoid(h W^T + a)) (pcd.py:37-49)."""
+        pack = self._pack.pack(self._RBM, need_bf16=False)
+        with torch.no_grad():
+            return _ops.half_step(pack, 1, hidden_states, _lib.MODE_SAMPLE, seed=self._seed,
+                                  chain_offset=self._chain_offset, half_step_idx=self._next_half_step())
+
+    # --------------------------------------------------------------------- k-step chain
+    def _run_chain(self, v, init_chains, k, step_offset):
+        lib = _lib.load()
+        dev = self._RBM.visible_bias.device
+        _lib.require_cuda(self._RBM.visible_bias, "RBM parameters")
+        B = self._batch_size
+        nV, nH = self._RBM.weights.shape
+        need_bf16 = self._variant != _lib.VARIANT_GENERAL
+        p, keep = self._pack.pack(self._RBM, need_bf16=need_bf16)
+        if v is None:
+            v = torch.empty((B, nV), dtype=torch.float32, device=dev)
+        h = torch.empty((B, nH), dtype=torch.float32, device=dev)
+        nbytes = lib.rbm_b200_block_gibbs_workspace(nV, nH, B, self._variant)
+        if nbytes and (self._workspace is None or self._workspace.numel() < nbytes
+                       or self._workspace.device != dev):
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = self._workspace if nbytes else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.rbm_b200_block_gibbs(
+                ctypes.byref(p), _ops._ptr(v), _ops._ptr(h), B, k, 1 if init_chains else 0, self._seed,
+                self._chain_offset, step_offset, self._variant, _ops._ptr(ws), nbytes, _ops._stream()),
+                "block_gibbs")
+        return v, h
+
+    def block_gibbs_sampling(self):
+        """Block Gibbs sampling (pcd.py:51-69). Returns (visible_states, hidden_states)."""
+        k = self.n_gibbs_sampling_steps
+        step_offset = self._half_steps
+        with torch.no_grad():
+            if self._persistent and self._MCState is not None:
+                v, h = self._run_chain(self._MCState.clone(), False, k, step_offset)
+            else:
+                v, h = self._run_chain(None, True, k, step_offset)
+        self._half_steps += 2 * k
+        if self._persistent:
+            self._MCState = v  # true PCD (the line the reference commented out, pcd.py:64)
+        return v, h
+
+    def _block_gibbs_with_uniforms(self, v0, uniforms_h, uniforms_v):
+        """Test hook: run k steps against injected uniforms [k,B,nH] / [k,B,nV] (fp32 W, GENERAL kernels)."""
+        lib = _lib.load()
+        p, keep = self._pack.pack(self._RBM, need_bf16=False)
+        v = _ops._f32c(v0, "v0").clone()
+        uh = _ops._f32c(uniforms_h, "uniforms_h"); uv = _ops._f32c(uniforms_v, "uniforms_v")
+        k, B = uh.shape[0], v.shape[0]
+        h = torch.empty((B, p.n_hidden), dtype=torch.float32, device=v.device)
+        with torch.cuda.device(v.device):
+            _lib.check(lib.rbm_b200_block_gibbs_injected(ctypes.byref(p), _ops._ptr(v), _ops._ptr(h), B, k,
+                                                         _ops._ptr(uh), _ops._ptr(uv), _ops._stream()),
+                       "block_gibbs_injected")
+        return v, h
+
+    # ------------------------------------------------------------- negative phase (a15)
+    def negative_phase(self, group=None):
+        """Run the chain and return (energy_exp, (S_vh, S_v, S_h)).
+
+        `energy_exp` equals GumBolt.energy_exp(v.detach(), h.detach()) (gumbolt.py:102-134) and
+        backpropagates -<v h^T>, -<v>, -<h> into (W, a, c) without the [B,nV,nH] broadcast.
+        With a process group the statistics are sum-allreduced over chain shards (NCCL).
+        """
+        v, h = self.block_gibbs_sampling()
+        world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(group)
+        S, sv, sh = _ops.negative_phase_stats(v, h, scale=1.0 / (self._batch_size * world))
+        if world > 1:
+            from .. import dist as _dist
+            S, sv, sh = _dist.allreduce_stats(S, sv, sh, group=group)
+        return _ops.energy_exp_from_stats(self._RBM, S, sv, sh), (S, sv, sh)

@@ -1,0 +1,159 @@
+/*
+ * rbm_b200.h — C ABI of the B200-native RBM block-Gibbs library (librbm_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of ezeeEric/DiVAE: block Gibbs
+ * sampling of the RBM prior.  The reference implements that path in Python/PyTorch
+ * (no FFI exists in the reference); each entry point below names the reference
+ * function it replaces (paths relative to the reference root).  The Python host
+ * side (divae_b200/) binds these with ctypes and mirrors the reference classes.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, integers.  No C++ or torch types.
+ *  - every pointer is a DEVICE pointer valid on the current CUDA device unless
+ *    stated otherwise; the caller owns every buffer; the library allocates
+ *    nothing persistent (workspaces are caller-provided).
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    never synchronises, never touches the default stream, and is CUDA-graph
+ *    capturable.
+ *  - return value: 0 = ok, < 0 = rbm_b200 error (RBM_B200_ERR_*), > 0 = cudaError_t.
+ *    rbm_b200_last_error() returns a thread-local description.
+ *  - matrices are row-major.  States are float32 holding exactly 0.0f / 1.0f at
+ *    the API boundary (the reference's dtype, models/samplers/pcd.py:35).
+ *  - there is no CPU fallback: without a CUDA device every compute entry fails.
+ *
+ * Random draws follow the counter-based Philox4x32-10 contract documented in
+ * DESIGN.md ("Draw contract") so results do not depend on tiling, kernel variant
+ * or GPU count:  counter = (unit_block, chain_id, half_step, tag), key = seed.
+ */
+#ifndef RBM_B200_H
+#define RBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBM_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RBM_B200_API __attribute__((visibility("default")))
+#else
+#define RBM_B200_API
+#endif
+
+enum {
+  RBM_B200_OK = 0,
+  RBM_B200_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, ...) */
+  RBM_B200_ERR_UNSUPPORTED = -2, /* shape / variant not supported by the requested kernel */
+  RBM_B200_ERR_WORKSPACE = -3,   /* workspace missing or too small */
+  RBM_B200_ERR_NO_DEVICE = -4    /* no CUDA device / wrong architecture (needs sm_100) */
+};
+
+/* Kernel variant selector for the k-step sampler. */
+enum {
+  RBM_B200_VARIANT_AUTO = 0,
+  RBM_B200_VARIANT_GENERAL = 1, /* fp32 SIMT, one launch per half-step, any shape, fp32 W */
+  RBM_B200_VARIANT_SMEM = 2,    /* persistent: W (bf16) resident in shared memory, states on chip */
+  RBM_B200_VARIANT_UMMA = 3     /* tcgen05/TMEM GEMM per half-step fed by TMA, bf16 {0,1} state tiles */
+};
+
+/* Epilogue mode of a single half-step. */
+enum {
+  RBM_B200_MODE_SAMPLE = 0,   /* Bernoulli draw with the Philox contract              */
+  RBM_B200_MODE_INJECTED = 1, /* Bernoulli draw against caller-supplied uniforms (test) */
+  RBM_B200_MODE_PROBS = 2     /* return probabilities, no draw (mean-field)           */
+};
+
+/* RBM parameters (reference: RBM.__init__, models/rbm/rbm.py:28-34).
+ * W is [n_visible, n_hidden] fp32; W_bf16 is the same matrix rounded to bf16
+ * (round-to-nearest-even), required by the SMEM and UMMA variants, else NULL. */
+typedef struct {
+  int32_t n_visible;
+  int32_t n_hidden;
+  const float *W;
+  const uint16_t *W_bf16;
+  const float *vbias; /* [n_visible]  "a" */
+  const float *hbias; /* [n_hidden]   "c" */
+} rbm_b200_params;
+
+/* Library / device queries (host only). */
+RBM_B200_API int rbm_b200_abi_version(void);
+RBM_B200_API const char *rbm_b200_last_error(void);
+/* Writes SM count, max opt-in shared memory per block (bytes) and compute
+ * capability (major*10+minor) of the current device. */
+RBM_B200_API int rbm_b200_device_info(int32_t *sm_count, int32_t *smem_optin, int32_t *cc);
+
+/* One conditional half-step on B rows.
+ *   direction 0: out[B,nH] = f(in[B,nV] W   + hbias)   PCD.hidden_samples   pcd.py:23-35, gibbsSampler.py:20-23
+ *   direction 1: out[B,nV] = f(in[B,nH] W^T + vbias)   PCD.visible_samples  pcd.py:37-49, gibbsSampler.py:25-28
+ * f = sigmoid then, by `mode`, a Philox draw (`p >= u`), a draw against
+ * `uniforms` ([B, n_out] fp32), or nothing (probabilities).  `in` may be
+ * real-valued.  fp32 W, fp32 accumulate.  `half_step` is the draw counter. */
+RBM_B200_API int rbm_b200_half_step(const rbm_b200_params *p, int direction, const float *in, float *out,
+                       int64_t B, int mode, const float *uniforms, uint64_t seed,
+                       uint64_t chain_offset, uint64_t half_step, void *stream);
+
+/* Bernoulli(1/2) chain (re-)initialisation on the device, replacing the CPU
+ * `rand >= rand` + H2D copy of PCD.__init__ / block_gibbs_sampling
+ * (pcd.py:16-17,59,66-67).  v[B,nV] <- {0,1}. */
+RBM_B200_API int rbm_b200_init_chains(float *v, int64_t B, int32_t n_visible, uint64_t seed,
+                         uint64_t chain_offset, uint64_t step_offset, void *stream);
+
+/* Bytes of caller-provided workspace rbm_b200_block_gibbs needs for this shape
+ * and variant (0 for the GENERAL variant). Host only. */
+RBM_B200_API size_t rbm_b200_block_gibbs_workspace(int32_t n_visible, int32_t n_hidden, int64_t B, int variant);
+
+/* k steps of block Gibbs sampling: v <- v0; k x { h ~ p(h|v); v ~ p(v|h) }.
+ * Replaces the loop of PCD.block_gibbs_sampling (pcd.py:51-69).  Returns the
+ * same pair as the reference: h was drawn from the previous v, v from that h.
+ *   v      [B,nV] in/out.  If init_chains != 0 the initial state is drawn on
+ *          the device (Bernoulli(1/2), as rbm_b200_init_chains) and the input
+ *          contents are ignored.
+ *   h      [B,nH] out.
+ *   step_offset  first half-step counter; half-step t of this call draws with
+ *          counter step_offset + t  (t = 2*step for h, 2*step+1 for v).
+ *   chain_offset global id of row 0 (rows are chains chain_offset .. +B-1), so
+ *          a shard of a larger job draws exactly what the unsharded job would.
+ *   variant      RBM_B200_VARIANT_*; AUTO picks SMEM for priors whose bf16 W
+ *          fits in shared memory, UMMA for large ones, GENERAL otherwise. */
+RBM_B200_API int rbm_b200_block_gibbs(const rbm_b200_params *p, float *v, float *h, int64_t B, int32_t k,
+                         int init_chains, uint64_t seed, uint64_t chain_offset,
+                         uint64_t step_offset, int variant, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
+/* Test hook: as rbm_b200_block_gibbs (GENERAL variant) but every draw compares
+ * against caller-supplied uniforms, laid out as the reference's torch.rand call
+ * order: for step s, uniforms_h[s] is [B,nH], uniforms_v[s] is [B,nV]
+ * (two dense arrays [k,B,nH] and [k,B,nV]). */
+RBM_B200_API int rbm_b200_block_gibbs_injected(const rbm_b200_params *p, float *v, float *h, int64_t B,
+                                  int32_t k, const float *uniforms_h, const float *uniforms_v,
+                                  void *stream);
+
+/* k mean-field sweeps on probabilities, no draws: GibbsSampler.gibbs_sampling
+ * (gibbsSampler.py:31-37).  left[B,nV] in/out, right[B,nH] out. */
+RBM_B200_API int rbm_b200_meanfield(const rbm_b200_params *p, float *left, float *right, int64_t B,
+                       int32_t k, void *stream);
+
+/* Per-sample energy E[b] = -v.a - h.c - sum_j (vW)_j h_j : RBM.energy
+ * (models/rbm/rbm.py:56-72).  v[B,nV], h[B,nH] may be real-valued.
+ * workspace: rbm_b200_energy_workspace(...) bytes. */
+RBM_B200_API size_t rbm_b200_energy_workspace(int32_t n_visible, int32_t n_hidden, int64_t B);
+RBM_B200_API int rbm_b200_energy(const rbm_b200_params *p, const float *v, const float *h, float *E,
+                    int64_t B, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Negative-phase statistics of a batch of chain states, the quantities autograd
+ * extracts from GumBolt.energy_exp / DiVAEPP.kl_divergence
+ * (models/autoencoders/gumbolt.py:102-134, dvaepp.py:141-159):
+ *   S_vh[nV,nH] = scale * sum_b v_b h_b^T,  S_v[nV] = scale * sum_b v_b,
+ *   S_h[nH] = scale * sum_b h_b.  Pass scale = 1/B_global so that a sum-allreduce
+ *   over chain shards yields the global means.  Outputs are overwritten. */
+RBM_B200_API int rbm_b200_negative_phase(const float *v, const float *h, int64_t B, int32_t n_visible,
+                            int32_t n_hidden, float scale, float *S_vh, float *S_v, float *S_h,
+                            void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBM_B200_H */
