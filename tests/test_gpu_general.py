@@ -104,9 +104,7 @@ def test_probabilities_and_meanfield_within_1e3_relative(golden):
     np.testing.assert_allclose(right.detach().cpu().numpy(), g["right"], rtol=1e-3, atol=1e-6)
     # 1-D real-valued start, as get_samples builds it (gibbsSampler.py:57-61)
     start = np.concatenate([-166 * g["starts"][0] + 88, -166 * g["starts"][1] + 88]).astype(np.float32)
-    gl, gr = gs.get_samples(approx_post_samples=[torch.from_numpy(start).to(DEV)][0:0] or [],
-                            n_latent_nodes=100, n_latent_hierarchy_lvls=4, n_gibbs_sampling_steps=0) \
-        if False else gs.gibbs_sampling(torch.from_numpy(start).to(DEV), int(g["gk"]))
+    gl, gr = gs.gibbs_sampling(torch.from_numpy(start).to(DEV), int(g["gk"]))
     assert gl.dim() == 1
     np.testing.assert_allclose(gl.detach().cpu().numpy(), g["gleft"], rtol=1e-3, atol=1e-6)
     np.testing.assert_allclose(gr.detach().cpu().numpy(), g["gright"], rtol=1e-3, atol=1e-6)
