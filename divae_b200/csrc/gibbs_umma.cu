@@ -1,9 +1,524 @@
+// UMMA variant: one Gibbs half-step = one tcgen05/TMEM GEMM fed by TMA, with the
+// bias + sigmoid + Philox + Bernoulli epilogue fused behind the accumulator.
+//
+//   H = [ sigmoid(V W + c) >= u ]      (models/samplers/pcd.py:32-35)   B operand MN-major
+//   V = [ sigmoid(H W^T + a) >= u ]    (models/samplers/pcd.py:46-49)   B operand K-major
+//
+// States live in HBM/L2 between half-steps as {0,1} bf16 tiles [chains_pad, units_pad]
+// (exact in bf16, so the tensor-core product with bf16 W is exact and the fp32 TMEM
+// accumulation differs from the oracle only in summation order).  W (bf16) is read from
+// ONE padded copy by both directions through two tensor maps.
+//
+// Kernel: persistent, warp-specialised, 1 CTA per SM, 128 x BLOCK_N output tile.
+//   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 4-stage mbarrier ring)
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16)
+//   warp 2      TMEM allocator (2 accumulator stages x BLOCK_N fp32 columns)
+//   warps 4-11  epilogue       (tcgen05.ld 32x32b.x32 -> ex2 + Philox + compare -> bf16 store)
+// The MMA of tile i+1 overlaps the epilogue of tile i through the two TMEM stages.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+#include "philox.cuh"
 #include "variants.h"
+
 namespace rbm {
-bool umma_variant_supported(int, int) { return false; }
-size_t umma_workspace_bytes(int, int, int64_t) { return 0; }
-int umma_block_gibbs(const rbm_b200_params*, float*, float*, int64_t, int, int, uint64_t, uint64_t, uint64_t, void*, size_t, cudaStream_t) {
-  set_error("UMMA variant not built"); return RBM_B200_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // one 128-byte swizzle atom of bf16 along K
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kNumEpilogueWarps = 8;
+constexpr int kNumThreads = 128 + kNumEpilogueWarps * 32;
+constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 64-bit shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version field = 1).
+//   K-major : rows of 128 B (64 bf16 along K), 8-row groups SBO = 1024 B apart; LBO unused (1).
+//   MN-major: 64 MN-elements (128 B) per k-row, 8-k groups SBO = 1024 B apart,
+//             64-element MN blocks LBO bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  d |= 2ull << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// 32-bit instruction descriptor: D fp32, A/B bf16, M x N, A K-major, B major selectable.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major) {
+  return (1u << 4)                       // c_format = F32
+         | (1u << 7)                     // a_format = BF16
+         | (1u << 10)                    // b_format = BF16
+         | (0u << 15)                    // a_major  = K
+         | ((b_mn_major ? 1u : 0u) << 16)  // b_major
+         | ((uint32_t)(N >> 3) << 17)    // n_dim
+         | ((uint32_t)(M >> 4) << 24);   // m_dim
+}
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers/tmem ptr + alignment slack
+};
+
+struct HalfStepArgs {
+  __nv_bfloat16* out;      // [rows_pad, ldo] destination state (bf16 {0,1})
+  const float* nbias;      // [>= n_tiles*BLOCK_N]  -bias * log2(e), zero padded
+  int ldo;                 // row pitch of out (elements)
+  int m_tiles, n_tiles;
+  int k_blocks;            // K_pad / 64
+  DrawCtx ctx;
+  uint64_t chain_offset;
+};
+
+// Decide one unit from its accumulator value: sigmoid(acc + bias) >= u  (philox.cuh contract).
+__device__ __forceinline__ uint32_t decide(float acc, float nb, uint32_t k16, const DrawCtx& ctx, uint32_t blk,
+                                           uint32_t chain, uint32_t slot) {
+  const float e = ex2_approx(fmaf(acc, -1.4426950408889634f, nb));
+  const float s = 1.0f + e;
+  const float kf = __uint_as_float(0x4B000000u | k16) - 8388608.0f;
+  const float t = kf * s;
+  if (t + s <= 65536.0f) return 1u;
+  if (t > 65536.0f) return 0u;
+  // 2^-16-probability tail: resolve with the refinement bits (kept out of line)
+  const float p = __frcp_rn(s);
+  const float y = p * 65536.0f;
+  const float fl = floorf(y);
+  if (fl > kf) return 1u;
+  if (fl < kf) return 0u;
+  const uint32_t e16 = field16(draw_block_extra(ctx, blk, chain), slot);
+  return ((y - fl) * 65536.0f >= (float)e16) ? 1u : 0u;
+}
+
+template <int BLOCK_N, bool B_MN_MAJOR>
+__global__ void __launch_bounds__(kNumThreads, 1)
+umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const HalfStepArgs args) {
+  using L = SmemLayout<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L::kBarOffset;
+  // barrier slots (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kBarOffset + 8 * (2 * kStages + 4));
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = args.m_tiles * args.n_tiles;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 or 512)
+
+  if (warp_idx == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), kNumEpilogueWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp_idx == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % args.n_tiles, m_blk = tile / args.n_tiles;
+        for (int kb = 0; kb < args.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * L::kStageBytes;
+          const uint32_t sb = sa + kABytes;
+          mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+          if (B_MN_MAJOR) {
+            // W[k rows][n cols]: one [64 x 64] box per 64-column MN block, 8 KB apart (LBO)
+#pragma unroll
+            for (int nb = 0; nb < BLOCK_N / 64; ++nb)
+              tma_load_2d(sb + nb * (BLOCK_K * 128), &tmap_b, full_bar(stage), n_blk * BLOCK_N + nb * 64, kb * BLOCK_K);
+          } else {
+            // W[n rows][k cols]: one [BLOCK_N x 64] box, rows of 128 B
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, B_MN_MAJOR);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(tmem_empty_bar(as), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < args.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * L::kStageBytes;
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bdesc = B_MN_MAJOR ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                              : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tmem_full_bar(as));   // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ================================= epilogue =================================
+    const int ew = warp_idx - 4;
+    const int quarter = warp_idx & 3;           // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                   // which half of the tile's columns
+    constexpr int kColsPerWarp = BLOCK_N / 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int n_blk = tile % args.n_tiles, m_blk = tile / args.n_tiles;
+      const int as = it & 1;
+      mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u);
+      tcgen05_fence_after();
+      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+      const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)row);
+      __nv_bfloat16* out_row = args.out + (size_t)row * args.ldo;
+#pragma unroll 1
+      for (int ch = 0; ch < kColsPerWarp / 32; ++ch) {
+        const int col_in_tile = half * kColsPerWarp + ch * 32;
+        const int col0 = n_blk * BLOCK_N + col_in_tile;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + col_in_tile), r);
+        tmem_ld_wait();
+        if (ch == kColsPerWarp / 32 - 1) {
+          // all of this warp's TMEM reads for the tile are done: hand the stage back
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+        }
+        if (col0 >= args.ldo) continue;  // tile overhang beyond the padded unit count: nothing to store
+        float nb[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.nbias + col0) + q);
+          nb[4 * q] = b4.x; nb[4 * q + 1] = b4.y; nb[4 * q + 2] = b4.z; nb[4 * q + 3] = b4.w;
+        }
+        uint32_t bits = 0;
+        const uint32_t blk0 = (uint32_t)(col0 >> 5) * 4u;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint4 w = draw_block(args.ctx, blk0 + b, chain);
+          const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            const int cc = 8 * (s >> 1) + 2 * b + (s & 1);
+            const uint32_t k16 = (s & 1) ? (words[s >> 1] >> 16) : (words[s >> 1] & 0xFFFFu);
+            bits |= decide(__uint_as_float(r[cc]), nb[cc], k16, args.ctx, blk0 + b, chain, (uint32_t)s) << cc;
+          }
+        }
+        // 32 units -> 32 bf16 {0,1} = 64 contiguous bytes of this chain's row
+        uint4* dst = reinterpret_cast<uint4*>(out_row + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t two = (bits >> (8 * q + 2 * j)) & 3u;
+            pk[j] = ((two & 1u) | ((two & 2u) << 15)) * 0x3F80u;  // bf16 1.0 = 0x3F80
+          }
+          dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------- helper kernels
+// fp32 [B, n] (row pitch n) -> bf16 [rows_pad, ld] zero padded
+__global__ void f32_to_bf16_padded(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t B, int n,
+                                   int64_t rows_pad, int ld) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_pad * ld) return;
+  const int64_t r = idx / ld;
+  const int c = (int)(idx % ld);
+  dst[idx] = __float2bfloat16((r < B && c < n) ? src[r * n + c] : 0.f);
+}
+// bf16 [rows_pad, ld] -> fp32 [B, n]
+__global__ void bf16_to_f32_crop(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t B, int n, int ld) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * n) return;
+  const int64_t r = idx / n;
+  const int c = (int)(idx % n);
+  dst[idx] = __bfloat162float(src[r * ld + c]);
+}
+__global__ void pad_w_kernel(const uint16_t* __restrict__ W, uint16_t* __restrict__ Wp, int nV, int nH, int nVp, int nHp) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)nVp * nHp) return;
+  const int i = (int)(idx / nHp), j = (int)(idx % nHp);
+  Wp[idx] = (i < nV && j < nH) ? W[(int64_t)i * nH + j] : (uint16_t)0;
+}
+__global__ void nbias_kernel(const float* __restrict__ bias, float* __restrict__ nb, int n, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) nb[i] = i < n ? -1.4426950408889634f * bias[i] : 0.f;
+}
+// Bernoulli(1/2) initial state straight into the bf16 state buffer (contract: 1 - (u16 >> 15), TAG_INIT)
+__global__ void init_chains_bf16_kernel(__nv_bfloat16* __restrict__ v, int64_t rows, int nV, int ld, DrawCtx ctx,
+                                        uint64_t chain_offset) {
+  const int nblk = ld / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * nblk) return;
+  const int64_t row = idx / nblk;
+  const int blk = (int)(idx % nblk);
+  const uint4 w = draw_block(ctx, (uint32_t)blk, (uint32_t)(chain_offset + (uint64_t)row));
+  const int base = (blk >> 2) * 32 + (blk & 3) * 2;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int c = base + (s >> 1) * 8 + (s & 1);
+    if (c < ld) v[row * (int64_t)ld + c] = __float2bfloat16((c < nV && !(field16(w, s) >> 15)) ? 1.f : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    RBM_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    RBM_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, RBM_B200_ERR_NO_DEVICE,
+                "cuTensorMapEncodeTiled is not available from the driver");
+    fn = (EncodeTiledFn)p;
+  }
+  *out = fn;
+  return 0;
+}
+
+// bf16 row-major [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128B swizzle
+int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn;
+  int rc = get_encode_fn(&fn);
+  if (rc) return rc;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RBM_REQUIRE(r == CUDA_SUCCESS, RBM_B200_ERR_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+struct Plan {
+  int nV, nH, nVp, nHp;      // padded to multiples of 64
+  int64_t rows_pad;          // chains padded to a multiple of 128
+  int bn_h, bn_v;            // BLOCK_N for the v->h and h->v half-steps
+  size_t off_W, off_nbh, off_nbv, off_V, off_H, total;
+};
+
+int pick_block_n(int n_pad) {
+  // fewest padded columns wins; ties go to the wider tile
+  const int w256 = round_up(n_pad, 256), w128 = round_up(n_pad, 128);
+  return (w128 < w256) ? 128 : 256;
+}
+
+Plan make_plan(int nV, int nH, int64_t B) {
+  Plan p;
+  p.nV = nV; p.nH = nH;
+  p.nVp = round_up(nV, 64); p.nHp = round_up(nH, 64);
+  p.rows_pad = ceil_div64(B, BLOCK_M) * BLOCK_M;
+  p.bn_h = pick_block_n(p.nHp); p.bn_v = pick_block_n(p.nVp);
+  auto align = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  size_t o = 0;
+  p.off_W = o; o = align(o + (size_t)p.nVp * p.nHp * 2);
+  p.off_nbh = o; o = align(o + (size_t)round_up(p.nHp, 256) * 4);
+  p.off_nbv = o; o = align(o + (size_t)round_up(p.nVp, 256) * 4);
+  p.off_V = o; o = align(o + (size_t)p.rows_pad * p.nVp * 2);
+  p.off_H = o; o = align(o + (size_t)p.rows_pad * p.nHp * 2);
+  p.total = o + 1024;  // slack to align the caller's pointer
+  return p;
+}
+
+template <int BLOCK_N, bool B_MN_MAJOR>
+int launch_half_step(const CUtensorMap& ta, const CUtensorMap& tb, const HalfStepArgs& a, int sm_count, cudaStream_t st) {
+  auto kern = umma_half_step_kernel<BLOCK_N, B_MN_MAJOR>;
+  static bool configured = false;
+  if (!configured) {
+    RBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BLOCK_N>::kTotal));
+    configured = true;
+  }
+  const int grid = std::min(a.m_tiles * a.n_tiles, sm_count);
+  kern<<<grid, kNumThreads, SmemLayout<BLOCK_N>::kTotal, st>>>(ta, tb, a);
+  return check_launch("umma_half_step_kernel");
+}
+
+}  // namespace
+
+bool umma_variant_supported(int nV, int nH) { return nV >= 1 && nH >= 1 && nV <= 16384 && nH <= 16384; }
+
+size_t umma_workspace_bytes(int nV, int nH, int64_t B) { return make_plan(nV, nH, B).total; }
+
+int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains,
+                     uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  const Plan pl = make_plan(p->n_visible, p->n_hidden, B);
+  RBM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, RBM_B200_ERR_WORKSPACE,
+              "UMMA variant needs %zu bytes of workspace, got %zu", pl.total, ws_bytes);
+  int dev = 0, sm_count = 0, cc_major = 0;
+  RBM_CUDA_TRY(cudaGetDevice(&dev));
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  RBM_REQUIRE(cc_major == 10, RBM_B200_ERR_NO_DEVICE, "UMMA variant needs an sm_100 device (got cc %d.x)", cc_major);
+
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  uint16_t* Wp = reinterpret_cast<uint16_t*>(base + pl.off_W);
+  float* nbh = reinterpret_cast<float*>(base + pl.off_nbh);
+  float* nbv = reinterpret_cast<float*>(base + pl.off_nbv);
+  __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(base + pl.off_V);
+  __nv_bfloat16* Hs = reinterpret_cast<__nv_bfloat16*>(base + pl.off_H);
+
+  // stage parameters: padded bf16 W, pre-scaled biases
+  {
+    const int64_t n = (int64_t)pl.nVp * pl.nHp;
+    pad_w_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W_bf16, Wp, pl.nV, pl.nH, pl.nVp, pl.nHp);
+    const int nh256 = round_up(pl.nHp, 256), nv256 = round_up(pl.nVp, 256);
+    nbias_kernel<<<ceil_div(nh256, 256), 256, 0, st>>>(p->hbias, nbh, pl.nH, nh256);
+    nbias_kernel<<<ceil_div(nv256, 256), 256, 0, st>>>(p->vbias, nbv, pl.nV, nv256);
+  }
+  // initial state
+  if (init_chains) {
+    const int64_t n = pl.rows_pad * (pl.nVp / 8);
+    init_chains_bf16_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(Vs, pl.rows_pad, pl.nV, pl.nVp,
+                                                                         make_draw_ctx(seed, step_offset, TAG_INIT), chain_offset);
+  } else {
+    const int64_t n = pl.rows_pad * pl.nVp;
+    f32_to_bf16_padded<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(v, Vs, B, pl.nV, pl.rows_pad, pl.nVp);
+  }
+  int rc = check_launch("umma staging kernels");
+  if (rc) return rc;
+
+  // tensor maps: states are K-major A operands; W is read MN-major (v->h) and K-major (h->v)
+  CUtensorMap tm_v, tm_h, tm_w_mn, tm_w_k;
+  if ((rc = make_tmap(&tm_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
+  if ((rc = make_tmap(&tm_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
+  if ((rc = make_tmap(&tm_w_mn, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&tm_w_k, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, (uint32_t)pl.bn_v))) return rc;
+
+  HalfStepArgs ah{}, av{};
+  ah.out = Hs; ah.nbias = nbh; ah.ldo = pl.nHp; ah.m_tiles = (int)(pl.rows_pad / BLOCK_M);
+  ah.n_tiles = ceil_div(pl.nHp, pl.bn_h); ah.k_blocks = pl.nVp / BLOCK_K; ah.chain_offset = chain_offset;
+  av.out = Vs; av.nbias = nbv; av.ldo = pl.nVp; av.m_tiles = ah.m_tiles;
+  av.n_tiles = ceil_div(pl.nVp, pl.bn_v); av.k_blocks = pl.nHp / BLOCK_K; av.chain_offset = chain_offset;
+
+  for (int s = 0; s < k; ++s) {
+    ah.ctx = make_draw_ctx(seed, step_offset + 2ull * s, TAG_GIBBS);
+    rc = pl.bn_h == 256 ? launch_half_step<256, true>(tm_v, tm_w_mn, ah, sm_count, st)
+                        : launch_half_step<128, true>(tm_v, tm_w_mn, ah, sm_count, st);
+    if (rc) return rc;
+    av.ctx = make_draw_ctx(seed, step_offset + 2ull * s + 1, TAG_GIBBS);
+    rc = pl.bn_v == 256 ? launch_half_step<256, false>(tm_h, tm_w_k, av, sm_count, st)
+                        : launch_half_step<128, false>(tm_h, tm_w_k, av, sm_count, st);
+    if (rc) return rc;
+  }
+  // back to the reference's dtype
+  {
+    const int64_t nv = B * pl.nV, nh = B * pl.nH;
+    bf16_to_f32_crop<<<(unsigned)ceil_div64(nv, 256), 256, 0, st>>>(Vs, v, B, pl.nV, pl.nVp);
+    if (k > 0) bf16_to_f32_crop<<<(unsigned)ceil_div64(nh, 256), 256, 0, st>>>(Hs, h, B, pl.nH, pl.nHp);
+  }
+  return check_launch("umma output conversion");
+}
+
+}  // namespace rbm
