@@ -13,7 +13,7 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 4-stage mbarrier ring)
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16)
 //   warp 2      TMEM allocator (2 accumulator stages x BLOCK_N fp32 columns)
-//   warps 4-11  epilogue       (tcgen05.ld 32x32b.x32 -> ex2 + Philox + compare -> bf16 store)
+//   warps 4-19  epilogue       (tcgen05.ld 32x32b.x16 -> ex2 + Philox + compare -> bf16 store)
 // The MMA of tile i+1 overlaps the epilogue of tile i through the two TMEM stages.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -31,7 +31,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // one 128-byte swizzle atom of bf16 along K
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
-constexpr int kNumEpilogueWarps = 8;
+constexpr int kNumEpilogueWarps = 16;  // 4 per TMEM lane quarter; each owns BLOCK_N/4 columns
 constexpr int kNumThreads = 128 + kNumEpilogueWarps * 32;
 constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
 
@@ -90,6 +90,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 64-bit shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version field = 1).
@@ -135,18 +143,29 @@ struct HalfStepArgs {
   uint64_t chain_offset;
 };
 
-// Decide one unit from its accumulator value: sigmoid(acc + bias) >= u  (philox.cuh contract).
-__device__ __forceinline__ uint32_t decide(float acc, float nb, uint32_t k16, const DrawCtx& ctx, uint32_t blk,
-                                           uint32_t chain, uint32_t slot) {
-  const float e = ex2_approx(fmaf(acc, -1.4426950408889634f, nb));
-  const float s = 1.0f + e;
-  const float kf = __uint_as_float(0x4B000000u | k16) - 8388608.0f;
-  const float t = kf * s;
-  if (t + s <= 65536.0f) return 1u;
-  if (t > 65536.0f) return 0u;
-  // 2^-16-probability tail: resolve with the refinement bits (kept out of line)
-  const float p = __frcp_rn(s);
-  const float y = p * 65536.0f;
+// Decision rule shared by the fast path and the exact path (philox.cuh contract, p = 1/s):
+//   d = 65536 - k16 * s.   d >= s  <=>  (k16+1) * s <= 65536  <=>  p*65536 >= k16+1  -> 1
+//                          d <  0  <=>   k16 * s    >  65536  <=>  p*65536 <  k16    -> 0
+//   0 <= d < s: the 16-bit field alone cannot decide (probability 2^-16 per draw).
+// For non-negative floats the bit patterns order like the values and negative floats have the
+// sign bit set, so "0 <= d < s" is ONE unsigned integer compare of the bit patterns.
+struct Decision { float d, s; };
+__device__ __forceinline__ Decision decision_terms(float acc, float nb, float kf) {
+  Decision r;
+  r.s = 1.0f + ex2_approx(fmaf(acc, -1.4426950408889634f, nb));  // 1 + e^-(acc+bias)
+  r.d = fmaf(-kf, r.s, 65536.0f);
+  return r;
+}
+
+// Exact path for a 16-unit span in which some unit was ambiguous (rare, kept out of line):
+// returns the 16 decisions as a bit mask.
+__device__ __noinline__ uint32_t resolve_exact(float acc, float nb, uint32_t k16, DrawCtx ctx, uint32_t blk,
+                                               uint32_t chain, uint32_t slot) {
+  const float kf = (float)k16;
+  const Decision q = decision_terms(acc, nb, kf);
+  if (q.d >= q.s) return 1u;
+  if (!(__float_as_uint(q.d) < __float_as_uint(q.s))) return 0u;
+  const float y = __frcp_rn(q.s) * 65536.0f;   // p * 65536, exact scaling
   const float fl = floorf(y);
   if (fl > kf) return 1u;
   if (fl < kf) return 0u;
@@ -251,10 +270,10 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
   } else if (warp_idx >= 4) {
     // ================================= epilogue =================================
-    const int ew = warp_idx - 4;
-    const int quarter = warp_idx & 3;           // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                   // which half of the tile's columns
-    constexpr int kColsPerWarp = BLOCK_N / 2;
+    const int quarter = warp_idx & 3;            // TMEM lane quarter this warp may access
+    const int cq = (warp_idx - 4) >> 2;          // which quarter of the tile's columns
+    constexpr int kColsPerWarp = BLOCK_N / 4;
+    constexpr int kGroups = kColsPerWarp / 32;   // 32-unit Philox groups per warp per tile
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int n_blk = tile % args.n_tiles, m_blk = tile / args.n_tiles;
@@ -265,49 +284,70 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)row);
       __nv_bfloat16* out_row = args.out + (size_t)row * args.ldo;
 #pragma unroll 1
-      for (int ch = 0; ch < kColsPerWarp / 32; ++ch) {
-        const int col_in_tile = half * kColsPerWarp + ch * 32;
+      for (int g = 0; g < kGroups; ++g) {
+        const int col_in_tile = cq * kColsPerWarp + g * 32;
         const int col0 = n_blk * BLOCK_N + col_in_tile;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + col_in_tile), r);
-        tmem_ld_wait();
-        if (ch == kColsPerWarp / 32 - 1) {
-          // all of this warp's TMEM reads for the tile are done: hand the stage back
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(as));
-        }
-        if (col0 >= args.ldo) continue;  // tile overhang beyond the padded unit count: nothing to store
-        float nb[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.nbias + col0) + q);
-          nb[4 * q] = b4.x; nb[4 * q + 1] = b4.y; nb[4 * q + 2] = b4.z; nb[4 * q + 3] = b4.w;
-        }
-        uint32_t bits = 0;
+        const bool live = col0 < args.ldo;   // tile overhang beyond the padded unit count
         const uint32_t blk0 = (uint32_t)(col0 >> 5) * 4u;
+        // four Philox calls cover the 32 units of this group (slot mapping: philox.cuh)
+        uint32_t w[4][4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const uint4 w = draw_block(args.ctx, blk0 + b, chain);
-          const uint32_t words[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            const int cc = 8 * (s >> 1) + 2 * b + (s & 1);
-            const uint32_t k16 = (s & 1) ? (words[s >> 1] >> 16) : (words[s >> 1] & 0xFFFFu);
-            bits |= decide(__uint_as_float(r[cc]), nb[cc], k16, args.ctx, blk0 + b, chain, (uint32_t)s) << cc;
-          }
+          const uint4 x = draw_block(args.ctx, blk0 + b, chain);
+          w[b][0] = x.x; w[b][1] = x.y; w[b][2] = x.z; w[b][3] = x.w;
         }
-        // 32 units -> 32 bf16 {0,1} = 64 contiguous bytes of this chain's row
-        uint4* dst = reinterpret_cast<uint4*>(out_row + col0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t two = (bits >> (8 * q + 2 * j)) & 3u;
-            pk[j] = ((two & 1u) | ((two & 2u) << 15)) * 0x3F80u;  // bf16 1.0 = 0x3F80
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + col_in_tile + 16 * hh), r);
+          tmem_ld_wait();
+          if (g == kGroups - 1 && hh == 1) {
+            // all of this warp's TMEM reads for the tile are done: hand the stage back
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(as));
           }
-          dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (!live) continue;
+          uint32_t pk[8];       // 16 units -> 16 bf16 {0,1}, packed in pairs
+          bool amb = false;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 nb4 = __ldg(reinterpret_cast<const float4*>(args.nbias + col0 + 16 * hh) + q4);
+            const float nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const int c16 = 4 * q4 + i4;           // column within this 16-wide half
+              const int cc = 16 * hh + c16;          // column within the 32-group
+              const int b = (cc & 7) >> 1;           // Philox block
+              const int slot = 2 * (cc >> 3) + (cc & 1);
+              const uint32_t word = w[b][slot >> 1];
+              // float(8388608 + k16) with one byte-permute, minus 2^23 -> exact float(k16)
+              const uint32_t mbits = (slot & 1) ? __byte_perm(word, 0x4B000000u, 0x7632) : __byte_perm(word, 0x4B000000u, 0x7610);
+              const float kf = __uint_as_float(mbits) - 8388608.0f;
+              const Decision q = decision_terms(__uint_as_float(r[c16]), nbv[i4], kf);
+              const bool one = q.d >= q.s;
+              amb = amb || (__float_as_uint(q.d) < __float_as_uint(q.s));
+              const uint32_t val = (c16 & 1) ? 0x3F800000u : 0x3F80u;   // bf16 1.0 in the high / low half
+              if (c16 & 1) pk[c16 >> 1] |= one ? val : 0u; else pk[c16 >> 1] = one ? val : 0u;
+            }
+          }
+          if (amb) {
+            // some unit of this span needs its refinement bits: redo the span on the exact path
+#pragma unroll
+            for (int c16 = 0; c16 < 16; ++c16) {
+              const int cc = 16 * hh + c16;
+              const int b = (cc & 7) >> 1, slot = 2 * (cc >> 3) + (cc & 1);
+              const uint32_t word = w[b][slot >> 1];
+              const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
+              const uint32_t one = resolve_exact(__uint_as_float(r[c16]), __ldg(args.nbias + col0 + cc), k16, args.ctx,
+                                                 blk0 + b, chain, (uint32_t)slot);
+              const uint32_t val = one ? ((c16 & 1) ? 0x3F800000u : 0x3F80u) : 0u;
+              if (c16 & 1) pk[c16 >> 1] |= val; else pk[c16 >> 1] = val;
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(out_row + col0 + 16 * hh);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
       }
     }
