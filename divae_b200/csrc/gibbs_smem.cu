@@ -1,9 +1,384 @@
+// SMEM variant: persistent k-step block Gibbs for small priors (nV, nH <= 256).
+//
+// One launch runs ALL 2k half-steps of PCD.block_gibbs_sampling (models/samplers/pcd.py:51-69):
+//   * W (bf16) and the pre-scaled biases are loaded into shared memory once per CTA;
+//   * chain states never leave the SM: they live as packed bits in shared memory (4 KB per
+//     128 chains) and, while being multiplied, as bf16 {0,1} MMA A-fragments in registers;
+//   * each half-step is  acc = state x W (mma.sync m16n8k16 bf16, fp32 accumulate, B fragments
+//     by ldmatrix / ldmatrix.trans from the ONE row-major copy of W),  then per unit:
+//     bias add, sigmoid via one ex2, Philox4x32-10 field, Bernoulli compare, bit pack.
+// The accumulator fragment layout of two adjacent n-tiles IS the A-fragment layout of the next
+// half-step's k-tile, so new states go registers -> bits -> registers with no transposition;
+// the Philox slot mapping (philox.cuh) gives every thread exactly its own 8 units per call.
+//
+// A chain group = 16 chains.  WN warps cooperate on one group (each owns a quarter/half/all
+// of the output units, 64-unit words) and exchange the new state through shared memory; a CTA
+// holds GROUPS groups.  WN=1 maximises throughput for many chains, WN=2/4 cuts the latency of
+// one half-step when there are few chains (BASELINE configs 2-3 are latency-bound).
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+#include "philox.cuh"
 #include "variants.h"
+
 namespace rbm {
-bool smem_variant_supported(int, int) { return false; }
+namespace {
+
+constexpr int kMaxUnits = 256;
+constexpr int kMaxWords = kMaxUnits / 64;
+constexpr float kNegLog2e = -1.4426950408889634f;
+
+struct SmemArgs {
+  const uint16_t* W;     // [nV, nH] bf16 row-major (global)
+  const float* vbias;
+  const float* hbias;
+  float* v;              // [B, nV] fp32 in/out
+  float* h;              // [B, nH] fp32 out
+  int64_t B;
+  int nV, nH;
+  int k;
+  int init_chains;
+  uint64_t seed, chain_offset, step_offset;
+  int wn;                // warps per chain group (1, 2 or 4)
+  int groups;            // chain groups per CTA
+  int64_t n_batches;     // ceil(B / (16 * groups))
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+  if (nthreads == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Exact decision for the rare ambiguous draw (same rule as gibbs_umma.cu / philox.cuh).
+__device__ __noinline__ uint32_t smem_resolve_exact(float acc, float nb, uint32_t k16, DrawCtx ctx, uint32_t blk,
+                                                    uint32_t chain, uint32_t slot) {
+  const float kf = (float)k16;
+  const float s = 1.0f + ex2_approx(fmaf(acc, kNegLog2e, nb));
+  const float d = fmaf(-kf, s, 65536.0f);
+  if (d >= s) return 1u;
+  if (!(__float_as_uint(d) < __float_as_uint(s))) return 0u;
+  const float y = __frcp_rn(s) * 65536.0f;
+  const float fl = floorf(y);
+  if (fl > kf) return 1u;
+  if (fl < kf) return 0u;
+  const uint32_t e16 = field16(draw_block_extra(ctx, blk, chain), slot);
+  return ((y - fl) * 65536.0f >= (float)e16) ? 1u : 0u;
+}
+
+// State word layout (one 32-bit word per lane per 64 units): for k-tile q (16 units) of the
+// word and A-fragment register r (0..3) the two bf16 halves come from bits (4q + r) and
+// (4q + r + 16), so   a[q][r] = ((word >> (4q + r)) & 0x00010001) * 0x3F80   (bf16 1.0 = 0x3F80).
+// Thread (g = lane/4, t = lane%4) owns rows g, g+8 and, in n-tile j of the word (8 units),
+// units 8j + 2t + e:  q = j/2,  r = 2*(j%2) + (row half),  e = unit parity.
+__device__ __forceinline__ int state_bit(int j, int rowhalf, int e) { return 4 * (j >> 1) + 2 * (j & 1) + rowhalf + 16 * e; }
+
+// One half-step for this warp: out words [ow_begin, ow_end) of  f(state_in x Wop + bias).
+//   TRANS_B = false: v -> h, Wop[k][n] = W[k][n]   (ldmatrix.trans on rows k)
+//   TRANS_B = true : h -> v, Wop[k][n] = W[n][k]   (ldmatrix on rows n)
+template <int MAXW, bool TRANS_B>
+__device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words, uint32_t* __restrict__ out_words,
+                                          int k_tiles, int n_units, int ow_begin, int ow_end, uint32_t w_smem,
+                                          int ldw_bytes, const float* __restrict__ nbias, const DrawCtx ctx,
+                                          uint32_t chain_lo, uint32_t chain_hi, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  // expand the input state bits into bf16 A fragments (registers)
+  uint32_t a[MAXW * 4][4];
+#pragma unroll
+  for (int w = 0; w < MAXW; ++w) {
+    const uint32_t word = (w * 4 < k_tiles) ? in_words[w * 32 + lane] : 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[w * 4 + q][r] = ((word >> (4 * q + r)) & 0x00010001u) * 0x3F80u;
+  }
+  // per-lane ldmatrix row/column offsets (matrix m = lane/8 of the x4 group)
+  const int m = lane >> 3, rr = lane & 7;
+  // TRANS_B=false: rows are k: row = k0 + (m&1)*8 + rr, col = n0 + (m>>1)*8
+  // TRANS_B=true : rows are n: row = n0 + (m>>1)*8 + rr, col = k0 + (m&1)*8
+  const int lrow = TRANS_B ? ((m >> 1) * 8 + rr) : ((m & 1) * 8 + rr);
+  const int lcol = TRANS_B ? ((m & 1) * 8) : ((m >> 1) * 8);
+
+  for (int ow = ow_begin; ow < ow_end; ++ow) {
+    const int n_base = ow * 64;
+    const int n_tiles16 = min(4, (n_units - n_base + 15) >> 4);  // live 16-unit column pairs in this word
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < MAXW * 4; ++kt) {
+      if (kt < k_tiles) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {       // 16-unit column pair p -> n-tiles 2p, 2p+1
+          if (p < n_tiles16) {
+            uint32_t b0, b1, b2, b3;
+            const int row = TRANS_B ? (n_base + p * 16 + lrow) : (kt * 16 + lrow);
+            const int col = TRANS_B ? (kt * 16 + lcol) : (n_base + p * 16 + lcol);
+            const uint32_t addr = w_smem + (uint32_t)(row * ldw_bytes + col * 2);
+            if (TRANS_B) ldmatrix_x4(addr, b0, b1, b2, b3);
+            else ldmatrix_x4_trans(addr, b0, b1, b2, b3);
+            mma_bf16_16816(acc[2 * p], a[kt], b0, b1);
+            mma_bf16_16816(acc[2 * p + 1], a[kt], b2, b3);
+          }
+        }
+      }
+    }
+    // epilogue: 2 halves of 32 units; per half one Philox call per owned row
+    uint32_t word = 0;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      if (hf * 2 < n_tiles16) {
+        const uint32_t blk = (uint32_t)((ow * 2 + hf) * 4 + t);
+        const uint4 x0 = draw_block(ctx, blk, chain_lo);
+        const uint4 x1 = draw_block(ctx, blk, chain_hi);
+        const uint32_t wlo[4] = {x0.x, x0.y, x0.z, x0.w};
+        const uint32_t whi[4] = {x1.x, x1.y, x1.z, x1.w};
+        bool amb = false;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = hf * 4 + jj;
+          const float2 nb = *reinterpret_cast<const float2*>(nbias + n_base + 8 * j + 2 * t);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = i & 1, rowhalf = i >> 1;
+            const uint32_t wd = rowhalf ? whi[jj] : wlo[jj];
+            const uint32_t mbits = e ? __byte_perm(wd, 0x4B000000u, 0x7632) : __byte_perm(wd, 0x4B000000u, 0x7610);
+            const float kf = __uint_as_float(mbits) - 8388608.0f;
+            const float s = 1.0f + ex2_approx(fmaf(acc[j][i], kNegLog2e, e ? nb.y : nb.x));
+            const float d = fmaf(-kf, s, 65536.0f);
+            amb = amb || (__float_as_uint(d) < __float_as_uint(s));
+            word |= (d >= s) ? (1u << state_bit(j, rowhalf, e)) : 0u;
+          }
+        }
+        if (amb) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = hf * 4 + jj;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int e = i & 1, rowhalf = i >> 1;
+              const uint32_t wd = rowhalf ? whi[jj] : wlo[jj];
+              const uint32_t k16 = e ? (wd >> 16) : (wd & 0xFFFFu);
+              const uint32_t one = smem_resolve_exact(acc[j][i], nbias[n_base + 8 * j + 2 * t + e], k16, ctx, blk,
+                                                      rowhalf ? chain_hi : chain_lo, (uint32_t)(2 * jj + e));
+              const uint32_t bit = 1u << state_bit(j, rowhalf, e);
+              word = one ? (word | bit) : (word & ~bit);
+            }
+          }
+        }
+      }
+    }
+    // units beyond n_units inside the last live 16-pair must stay 0 (they are K padding next half-step)
+    if (n_base + 64 > n_units) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (n_base + 8 * j + 2 * t + e >= n_units) word &= ~((1u << state_bit(j, 0, e)) | (1u << state_bit(j, 1, e)));
+    }
+    out_words[ow * 32 + lane] = word;
+  }
+}
+
+template <int MAXW>
+__global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int nV = args.nV, nH = args.nH;
+  const int nVp = round_up(nV, 16), nHp = round_up(nH, 16);
+  const int ldw = nHp + 8;                   // +16 B row pad: conflict-free ldmatrix in both directions
+  const int ldw_bytes = ldw * 2;
+  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(smem);
+  float* nbh = reinterpret_cast<float*>(smem + (size_t)nVp * ldw_bytes);
+  float* nbv = nbh + kMaxUnits;
+  uint32_t* vbits = reinterpret_cast<uint32_t*>(nbv + kMaxUnits);   // [groups][kMaxWords][32]
+  uint32_t* hbits = vbits + args.groups * kMaxWords * 32;
+
+  const int tid = threadIdx.x;
+  // ---- stage W (zero padded) and the pre-scaled biases once per CTA
+  if ((nH & 7) == 0 && (reinterpret_cast<uintptr_t>(args.W) & 15) == 0) {
+    const int chunks = nH >> 3;                       // 16-byte chunks per row
+    for (int idx = tid; idx < nV * chunks; idx += blockDim.x) {
+      const int i = idx / chunks, c8 = idx % chunks;
+      *reinterpret_cast<uint4*>(Ws + (size_t)i * ldw + 8 * c8) =
+          __ldg(reinterpret_cast<const uint4*>(args.W + (size_t)i * nH) + c8);
+    }
+    const int padc = ldw - nH;                        // zero the column pad and the row pad
+    for (int idx = tid; idx < nV * padc; idx += blockDim.x)
+      reinterpret_cast<uint16_t*>(Ws)[(idx / padc) * ldw + nH + idx % padc] = 0;
+    for (int idx = tid + nV * ldw; idx < nVp * ldw; idx += blockDim.x) reinterpret_cast<uint16_t*>(Ws)[idx] = 0;
+  } else {
+    for (int idx = tid; idx < nVp * ldw; idx += blockDim.x) {
+      const int i = idx / ldw, j = idx % ldw;
+      uint16_t val = 0;
+      if (i < nV && j < nH) val = args.W[(size_t)i * nH + j];
+      reinterpret_cast<uint16_t*>(Ws)[idx] = val;
+    }
+  }
+  for (int i = tid; i < kMaxUnits; i += blockDim.x) {
+    nbh[i] = i < nH ? kNegLog2e * args.hbias[i] : 0.f;
+    nbv[i] = i < nV ? kNegLog2e * args.vbias[i] : 0.f;
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wn = args.wn;
+  const int grp = warp / wn;             // chain group of this warp inside the CTA
+  const int wsub = warp % wn;            // position inside the group's warp team
+  const bool active_warp = grp < args.groups;
+  const int g = lane >> 2, t = lane & 3;
+  const int vwords = (nV + 63) >> 6, hwords = (nH + 63) >> 6;
+  const int vt = (nV + 15) >> 4, ht = (nH + 15) >> 4;  // k-tiles per side
+  // split of output words among the team
+  const int h_per = (hwords + wn - 1) / wn, v_per = (vwords + wn - 1) / wn;
+  const int h_begin = min(hwords, wsub * h_per), h_end = min(hwords, h_begin + h_per);
+  const int v_begin = min(vwords, wsub * v_per), v_end = min(vwords, v_begin + v_per);
+  const uint32_t w_smem = (uint32_t)__cvta_generic_to_shared(Ws);
+  uint32_t* myv = vbits + grp * kMaxWords * 32;
+  uint32_t* myh = hbits + grp * kMaxWords * 32;
+  const int bar_id = 1 + grp, bar_threads = 32 * wn;
+
+  for (int64_t batch = blockIdx.x; batch < args.n_batches; batch += gridDim.x) {
+    if (active_warp) {
+      const int64_t row0 = (batch * args.groups + grp) * 16;
+      const int64_t r_lo = row0 + g, r_hi = row0 + g + 8;
+      const uint32_t chain_lo = (uint32_t)(args.chain_offset + (uint64_t)r_lo);
+      const uint32_t chain_hi = (uint32_t)(args.chain_offset + (uint64_t)r_hi);
+      // ---- initial visible state -> bits (this warp's share of the words)
+      for (int ow = v_begin; ow < v_end; ++ow) {
+        uint32_t word = 0;
+        if (args.init_chains) {
+          const DrawCtx ictx = make_draw_ctx(args.seed, args.step_offset, TAG_INIT);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const uint32_t blk = (uint32_t)((ow * 2 + hf) * 4 + t);
+            const uint4 x0 = draw_block(ictx, blk, chain_lo);
+            const uint4 x1 = draw_block(ictx, blk, chain_hi);
+            const uint32_t wlo[4] = {x0.x, x0.y, x0.z, x0.w}, whi[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int e = i & 1, rowhalf = i >> 1, j = hf * 4 + jj;
+                const uint32_t wd = rowhalf ? whi[jj] : wlo[jj];
+                const uint32_t f = e ? (wd >> 16) : (wd & 0xFFFFu);
+                const int unit = ow * 64 + 8 * j + 2 * t + e;
+                if (unit < nV && !(f >> 15)) word |= 1u << state_bit(j, rowhalf, e);
+              }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int e = i & 1, rowhalf = i >> 1;
+              const int unit = ow * 64 + 8 * j + 2 * t + e;
+              const int64_t r = rowhalf ? r_hi : r_lo;
+              if (unit < nV && r < args.B && args.v[r * nV + unit] > 0.5f) word |= 1u << state_bit(j, rowhalf, e);
+            }
+        }
+        myv[ow * 32 + lane] = word;
+      }
+      group_barrier(bar_id, bar_threads);
+      // ---- 2k half-steps, all on chip
+      for (int s = 0; s < args.k; ++s) {
+        const DrawCtx ch = make_draw_ctx(args.seed, args.step_offset + 2ull * s, TAG_GIBBS);
+        half_step<MAXW, false>(myv, myh, vt, nH, h_begin, h_end, w_smem, ldw_bytes, nbh, ch, chain_lo, chain_hi, lane);
+        group_barrier(bar_id, bar_threads);
+        const DrawCtx cv = make_draw_ctx(args.seed, args.step_offset + 2ull * s + 1, TAG_GIBBS);
+        half_step<MAXW, true>(myh, myv, ht, nV, v_begin, v_end, w_smem, ldw_bytes, nbv, cv, chain_lo, chain_hi, lane);
+        group_barrier(bar_id, bar_threads);
+      }
+      // ---- final states back to the reference's dtype (fp32 {0,1})
+      for (int side = 0; side < 2; ++side) {
+        const uint32_t* bits = side ? myh : myv;
+        float* out = side ? args.h : args.v;
+        const int n = side ? nH : nV;
+        const int wb = side ? h_begin : v_begin, we = side ? h_end : v_end;
+        if (side == 1 && args.k == 0) continue;
+        for (int ow = wb; ow < we; ++ow) {
+          const uint32_t word = bits[ow * 32 + lane];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int rowhalf = 0; rowhalf < 2; ++rowhalf) {
+              const int64_t r = rowhalf ? r_hi : r_lo;
+              const int unit = ow * 64 + 8 * j + 2 * t;
+              if (r < args.B) {
+                const float f0 = (word >> state_bit(j, rowhalf, 0)) & 1u ? 1.f : 0.f;
+                const float f1 = (word >> state_bit(j, rowhalf, 1)) & 1u ? 1.f : 0.f;
+                if (unit < n) out[r * n + unit] = f0;
+                if (unit + 1 < n) out[r * n + unit + 1] = f1;
+              }
+            }
+        }
+      }
+      group_barrier(bar_id, bar_threads);   // bits buffers are reused by the next batch
+    }
+  }
+}
+
+size_t smem_bytes_needed(int nV, int nH, int groups) {
+  const int nVp = round_up(nV, 16), nHp = round_up(nH, 16);
+  return (size_t)nVp * (nHp + 8) * 2 + 2 * kMaxUnits * sizeof(float) + (size_t)2 * groups * kMaxWords * 32 * sizeof(uint32_t);
+}
+
+}  // namespace
+
+bool smem_variant_supported(int nV, int nH) { return nV >= 1 && nH >= 1 && nV <= kMaxUnits && nH <= kMaxUnits; }
+
 size_t smem_workspace_bytes(int, int, int64_t) { return 0; }
-int smem_block_gibbs(const rbm_b200_params*, float*, float*, int64_t, int, int, uint64_t, uint64_t, uint64_t, void*, size_t, cudaStream_t) {
-  set_error("SMEM variant not built"); return RBM_B200_ERR_UNSUPPORTED;
+
+int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains, uint64_t seed,
+                     uint64_t chain_offset, uint64_t step_offset, void*, size_t, cudaStream_t st) {
+  RBM_REQUIRE(smem_variant_supported(p->n_visible, p->n_hidden), RBM_B200_ERR_UNSUPPORTED,
+              "SMEM variant supports priors up to %d x %d units, got %d x %d", kMaxUnits, kMaxUnits, p->n_visible,
+              p->n_hidden);
+  int dev = 0, sm_count = 0;
+  RBM_CUDA_TRY(cudaGetDevice(&dev));
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  SmemArgs a{};
+  a.W = p->W_bf16; a.vbias = p->vbias; a.hbias = p->hbias; a.v = v; a.h = h; a.B = B;
+  a.nV = p->n_visible; a.nH = p->n_hidden; a.k = k; a.init_chains = init_chains;
+  a.seed = seed; a.chain_offset = chain_offset; a.step_offset = step_offset;
+  const int vwords = ceil_div(a.nV, 64), hwords = ceil_div(a.nH, 64);
+  const int maxw = std::max(vwords, hwords);
+  const int64_t n_groups = ceil_div64(B, 16);
+  // few chains -> split each group's units over more warps (latency); many chains -> 1 warp per group
+  int wn = 1;
+  const int wn_cap = std::min(vwords, hwords);
+  while (wn * 2 <= wn_cap && wn * 2 <= 4 && n_groups * wn < (int64_t)sm_count * 8) wn *= 2;
+  int groups = 8 / wn;
+  while (groups > 1 && ceil_div64(n_groups, groups) < sm_count) groups >>= 1;
+  a.wn = wn; a.groups = groups;
+  a.n_batches = ceil_div64(n_groups, groups);
+  const size_t smem = smem_bytes_needed(a.nV, a.nH, groups);
+  const int grid = (int)std::min<int64_t>(a.n_batches, sm_count);
+  const int threads = 32 * wn * groups;
+  auto launch = [&](auto kern) -> int {
+    RBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(a);
+    return check_launch("smem_gibbs_kernel");
+  };
+  if (maxw <= 1) return launch(smem_gibbs_kernel<1>);
+  if (maxw <= 2) return launch(smem_gibbs_kernel<2>);
+  return launch(smem_gibbs_kernel<4>);
 }
-}
+
+}  // namespace rbm
