@@ -117,6 +117,10 @@ class _Energy(torch.autograd.Function):
         lib = _lib.load()
         p, keep = pack
         v = _f32c(v, "energy input"); h = _f32c(h, "energy input")
+        if v.dim() != 2 or h.dim() != 2 or v.shape[1] != p.n_visible or h.shape[1] != p.n_hidden or v.shape[0] != h.shape[0]:
+            # the reference fails here inside torch.matmul (rbm.py:68-70)
+            raise RuntimeError("size mismatch: energy got v %s, h %s for an RBM of %d x %d units"
+                               % (tuple(v.shape), tuple(h.shape), p.n_visible, p.n_hidden))
         B = v.shape[0]
         E = torch.empty(B, dtype=torch.float32, device=v.device)
         nbytes = lib.rbm_b200_energy_workspace(p.n_visible, p.n_hidden, B)
@@ -146,6 +150,8 @@ def negative_phase_stats(v, h, scale=None):
     """(S_vh, S_v, S_h) = scale * (V^T H, sum V, sum H); scale defaults to 1/B (means)."""
     lib = _lib.load()
     v = _f32c(v, "visible states"); h = _f32c(h, "hidden states")
+    if v.dim() != 2 or h.dim() != 2 or v.shape[0] != h.shape[0]:
+        raise RuntimeError("size mismatch: statistics need v [B,nV] and h [B,nH]")
     B, nV = v.shape
     nH = h.shape[1]
     if scale is None:

@@ -204,4 +204,27 @@ int rbm_b200_negative_phase(const float* v, const float* h, int64_t B, int32_t n
   return general_negative_phase(v, h, B, n_visible, n_hidden, scale, S_vh, S_v, S_h, (cudaStream_t)stream);
 }
 
+size_t rbm_b200_ais_workspace(int32_t n_visible, int32_t n_hidden, int64_t n_chains) {
+  if (n_chains <= 0 || n_visible <= 0 || n_hidden <= 0) return 0;
+  return umma_ais_workspace_bytes(n_visible, n_hidden, n_chains);
+}
+
+int rbm_b200_ais_run(const rbm_b200_params* p, int64_t n_chains, const double* betas, int32_t n_betas,
+                     uint64_t seed, uint64_t chain_offset, double* logw, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  int rc = check_params(p, false);
+  if (rc) return rc;
+  RBM_REQUIRE(p->W_bf16 != nullptr, RBM_B200_ERR_INVALID, "AIS needs W_bf16");
+  RBM_REQUIRE(n_chains >= 0, RBM_B200_ERR_INVALID, "negative chain count");
+  RBM_REQUIRE(betas != nullptr && n_betas >= 2, RBM_B200_ERR_INVALID, "need at least two betas");
+  RBM_REQUIRE(betas[0] == 0.0 && betas[n_betas - 1] == 1.0, RBM_B200_ERR_INVALID, "betas must run from 0 to 1");
+  for (int i = 1; i < n_betas; ++i)
+    RBM_REQUIRE(betas[i] > betas[i - 1], RBM_B200_ERR_INVALID, "betas must be strictly increasing");
+  if (n_chains == 0) return 0;
+  RBM_REQUIRE(logw != nullptr, RBM_B200_ERR_INVALID, "logw is NULL");
+  if ((rc = require_device())) return rc;
+  return umma_ais_run(p, n_chains, betas, n_betas, seed, chain_offset, logw, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -96,7 +96,7 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
                                           int k_tiles, int n_units, int ow_begin, int ow_end, uint32_t w_smem,
                                           int ldw_bytes, const float* __restrict__ nbias, const DrawCtx ctx,
                                           uint32_t chain_lo, uint32_t chain_hi, int lane) {
-  const int g = lane >> 2, t = lane & 3;
+  const int t = lane & 3;
   // expand the input state bits into bf16 A fragments (registers)
   uint32_t a[MAXW * 4][4];
 #pragma unroll

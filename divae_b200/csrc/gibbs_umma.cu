@@ -79,7 +79,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+[[maybe_unused]] __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -139,9 +139,25 @@ struct HalfStepArgs {
   int ldo;                 // row pitch of out (elements)
   int m_tiles, n_tiles;
   int k_blocks;            // K_pad / 64
+  int n_valid;             // real (unpadded) number of output units
   DrawCtx ctx;
   uint64_t chain_offset;
+  // annealed (AIS) epilogues only: arg = acc * scale + nbias * bmul
+  float scale;             // -log2(e) * beta_k
+  float bmul;              // beta_k on the hidden step (bias c is annealed), 1 on the visible step
+  float ratio;             // beta_{k-1} / beta_k
+  float* wpart;            // [rows_pad, wpart_ld] running log-weight partials (log2 units)
+  int wpart_ld;
 };
+
+// Epilogue flavours
+enum { EPI_GIBBS = 0, EPI_ANNEALED = 1, EPI_AIS_WEIGHT = 2 };
+
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Decision rule shared by the fast path and the exact path (philox.cuh contract, p = 1/s):
 //   d = 65536 - k16 * s.   d >= s  <=>  (k16+1) * s <= 65536  <=>  p*65536 >= k16+1  -> 1
@@ -150,19 +166,19 @@ struct HalfStepArgs {
 // For non-negative floats the bit patterns order like the values and negative floats have the
 // sign bit set, so "0 <= d < s" is ONE unsigned integer compare of the bit patterns.
 struct Decision { float d, s; };
-__device__ __forceinline__ Decision decision_terms(float acc, float nb, float kf) {
+// arg = -log2(e) * pre-activation, so 2^arg = e^-x and s = 1 + e^-x = 1/p
+__device__ __forceinline__ Decision decision_terms(float arg, float kf) {
   Decision r;
-  r.s = 1.0f + ex2_approx(fmaf(acc, -1.4426950408889634f, nb));  // 1 + e^-(acc+bias)
+  r.s = 1.0f + ex2_approx(arg);
   r.d = fmaf(-kf, r.s, 65536.0f);
   return r;
 }
 
-// Exact path for a 16-unit span in which some unit was ambiguous (rare, kept out of line):
-// returns the 16 decisions as a bit mask.
-__device__ __noinline__ uint32_t resolve_exact(float acc, float nb, uint32_t k16, DrawCtx ctx, uint32_t blk,
-                                               uint32_t chain, uint32_t slot) {
+// Exact path for a unit of a span in which some unit was ambiguous (rare, kept out of line).
+__device__ __noinline__ uint32_t resolve_exact(float arg, uint32_t k16, DrawCtx ctx, uint32_t blk, uint32_t chain,
+                                               uint32_t slot) {
   const float kf = (float)k16;
-  const Decision q = decision_terms(acc, nb, kf);
+  const Decision q = decision_terms(arg, kf);
   if (q.d >= q.s) return 1u;
   if (!(__float_as_uint(q.d) < __float_as_uint(q.s))) return 0u;
   const float y = __frcp_rn(q.s) * 65536.0f;   // p * 65536, exact scaling
@@ -173,7 +189,7 @@ __device__ __noinline__ uint32_t resolve_exact(float acc, float nb, uint32_t k16
   return ((y - fl) * 65536.0f >= (float)e16) ? 1u : 0u;
 }
 
-template <int BLOCK_N, bool B_MN_MAJOR>
+template <int BLOCK_N, bool B_MN_MAJOR, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const HalfStepArgs args) {
@@ -283,6 +299,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const int row = m_blk * BLOCK_M + quarter * 32 + lane;
       const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)row);
       __nv_bfloat16* out_row = args.out + (size_t)row * args.ldo;
+      float wsum = 0.f;   // EPI_AIS_WEIGHT: this thread's log-weight increment over its columns (log2 units)
 #pragma unroll 1
       for (int g = 0; g < kGroups; ++g) {
         const int col_in_tile = cq * kColsPerWarp + g * 32;
@@ -324,7 +341,17 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               // float(8388608 + k16) with one byte-permute, minus 2^23 -> exact float(k16)
               const uint32_t mbits = (slot & 1) ? __byte_perm(word, 0x4B000000u, 0x7632) : __byte_perm(word, 0x4B000000u, 0x7610);
               const float kf = __uint_as_float(mbits) - 8388608.0f;
-              const Decision q = decision_terms(__uint_as_float(r[c16]), nbv[i4], kf);
+              const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbv[i4])
+                                                 : fmaf(__uint_as_float(r[c16]), args.scale, nbv[i4] * args.bmul);
+              const Decision q = decision_terms(arg, kf);
+              if (EPI == EPI_AIS_WEIGHT) {
+                // log p*_k(v) - log p*_{k-1}(v), hidden-unit term: softplus(b_k x) - softplus(b_{k-1} x),
+                // in log2 units: softplus(bx)/ln2 = -arg + lg2(1 + 2^arg); clamped so 2^arg stays finite
+                const float ak = fminf(arg, 80.0f);
+                const float akm1 = ak * args.ratio;
+                if (col0 + cc < args.n_valid)
+                  wsum += (akm1 - ak) + lg2_approx(fminf(q.s, 1.2089258e24f)) - lg2_approx(1.0f + ex2_approx(akm1));
+              }
               const bool one = q.d >= q.s;
               amb = amb || (__float_as_uint(q.d) < __float_as_uint(q.s));
               const uint32_t val = (c16 & 1) ? 0x3F800000u : 0x3F80u;   // bf16 1.0 in the high / low half
@@ -339,8 +366,10 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               const int b = (cc & 7) >> 1, slot = 2 * (cc >> 3) + (cc & 1);
               const uint32_t word = w[b][slot >> 1];
               const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
-              const uint32_t one = resolve_exact(__uint_as_float(r[c16]), __ldg(args.nbias + col0 + cc), k16, args.ctx,
-                                                 blk0 + b, chain, (uint32_t)slot);
+              const float nbx = __ldg(args.nbias + col0 + cc);
+              const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbx)
+                                                 : fmaf(__uint_as_float(r[c16]), args.scale, nbx * args.bmul);
+              const uint32_t one = resolve_exact(arg, k16, args.ctx, blk0 + b, chain, (uint32_t)slot);
               const uint32_t val = one ? ((c16 & 1) ? 0x3F800000u : 0x3F80u) : 0u;
               if (c16 & 1) pk[c16 >> 1] |= val; else pk[c16 >> 1] = val;
             }
@@ -349,6 +378,11 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
+      }
+      if (EPI == EPI_AIS_WEIGHT) {
+        // exactly one thread owns (row, slot) in a launch: plain read-modify-write, deterministic
+        float* slot_ptr = args.wpart + (size_t)row * args.wpart_ld + (n_blk * 4 + cq);
+        *slot_ptr += wsum;
       }
     }
   }
@@ -406,6 +440,35 @@ __global__ void init_chains_bf16_kernel(__nv_bfloat16* __restrict__ v, int64_t r
   }
 }
 
+// AIS initial state v ~ p_A = Bernoulli(sigmoid(a)) (base-rate model with a_A = a), TAG_AIS_INIT
+__global__ void ais_init_kernel(__nv_bfloat16* __restrict__ v, int64_t rows, int nV, int ld,
+                                const float* __restrict__ nbias_v, DrawCtx ctx, uint64_t chain_offset) {
+  const int nblk = ld / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * nblk) return;
+  const int64_t row = idx / nblk;
+  const int blk = (int)(idx % nblk);
+  const uint32_t chain = (uint32_t)(chain_offset + (uint64_t)row);
+  const uint4 w = draw_block(ctx, (uint32_t)blk, chain);
+  const int base = (blk >> 2) * 32 + (blk & 3) * 2;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int c = base + (s >> 1) * 8 + (s & 1);
+    if (c >= ld) continue;
+    uint32_t one = 0;
+    if (c < nV) one = resolve_exact(nbias_v[c], field16(w, s), ctx, (uint32_t)blk, chain, (uint32_t)s);
+    v[row * (int64_t)ld + c] = __float2bfloat16(one ? 1.f : 0.f);
+  }
+}
+// logw[b] = ln2 * sum_slots wpart[b][slot]   (fp64 sum of the fp32 running partials)
+__global__ void ais_reduce_kernel(const float* __restrict__ wpart, int ld, int64_t B, double* __restrict__ logw) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double s = 0.0;
+  for (int i = 0; i < ld; ++i) s += (double)wpart[b * ld + i];
+  logw[b] = s * 0.6931471805599453;
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -445,7 +508,8 @@ struct Plan {
   int nV, nH, nVp, nHp;      // padded to multiples of 64
   int64_t rows_pad;          // chains padded to a multiple of 128
   int bn_h, bn_v;            // BLOCK_N for the v->h and h->v half-steps
-  size_t off_W, off_nbh, off_nbv, off_V, off_H, total;
+  size_t off_W, off_nbh, off_nbv, off_V, off_H, off_wpart, total;
+  int wpart_ld;              // AIS log-weight partial slots per chain: 4 per hidden-side N tile
 };
 
 int pick_block_n(int n_pad) {
@@ -467,13 +531,15 @@ Plan make_plan(int nV, int nH, int64_t B) {
   p.off_nbv = o; o = align(o + (size_t)round_up(p.nVp, 256) * 4);
   p.off_V = o; o = align(o + (size_t)p.rows_pad * p.nVp * 2);
   p.off_H = o; o = align(o + (size_t)p.rows_pad * p.nHp * 2);
+  p.wpart_ld = 4 * ceil_div(p.nHp, p.bn_h);
+  p.off_wpart = o; o = align(o + (size_t)p.rows_pad * p.wpart_ld * 4);
   p.total = o + 1024;  // slack to align the caller's pointer
   return p;
 }
 
-template <int BLOCK_N, bool B_MN_MAJOR>
+template <int BLOCK_N, bool B_MN_MAJOR, int EPI = EPI_GIBBS>
 int launch_half_step(const CUtensorMap& ta, const CUtensorMap& tb, const HalfStepArgs& a, int sm_count, cudaStream_t st) {
-  auto kern = umma_half_step_kernel<BLOCK_N, B_MN_MAJOR>;
+  auto kern = umma_half_step_kernel<BLOCK_N, B_MN_MAJOR, EPI>;
   static bool configured = false;
   if (!configured) {
     RBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BLOCK_N>::kTotal));
@@ -538,9 +604,9 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
 
   HalfStepArgs ah{}, av{};
   ah.out = Hs; ah.nbias = nbh; ah.ldo = pl.nHp; ah.m_tiles = (int)(pl.rows_pad / BLOCK_M);
-  ah.n_tiles = ceil_div(pl.nHp, pl.bn_h); ah.k_blocks = pl.nVp / BLOCK_K; ah.chain_offset = chain_offset;
+  ah.n_tiles = ceil_div(pl.nHp, pl.bn_h); ah.k_blocks = pl.nVp / BLOCK_K; ah.chain_offset = chain_offset; ah.n_valid = pl.nH;
   av.out = Vs; av.nbias = nbv; av.ldo = pl.nVp; av.m_tiles = ah.m_tiles;
-  av.n_tiles = ceil_div(pl.nVp, pl.bn_v); av.k_blocks = pl.nHp / BLOCK_K; av.chain_offset = chain_offset;
+  av.n_tiles = ceil_div(pl.nVp, pl.bn_v); av.k_blocks = pl.nHp / BLOCK_K; av.chain_offset = chain_offset; av.n_valid = pl.nV;
 
   for (int s = 0; s < k; ++s) {
     ah.ctx = make_draw_ctx(seed, step_offset + 2ull * s, TAG_GIBBS);
@@ -559,6 +625,79 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
     if (k > 0) bf16_to_f32_crop<<<(unsigned)ceil_div64(nh, 256), 256, 0, st>>>(Hs, h, B, pl.nH, pl.nHp);
   }
   return check_launch("umma output conversion");
+}
+
+size_t umma_ais_workspace_bytes(int nV, int nH, int64_t M) { return make_plan(nV, nH, M).total; }
+
+// Annealed importance sampling (Salakhutdinov & Murray 2008, RBM form).  The
+// reference has no estimator (models/rbm/rbm.py:51-54 returns a literal); the CPU restatement
+// is oracle/rbm_oracle.py:ais_logZ.  Per beta step: ONE GEMM x = vW + c feeds both the weight
+// increment sum_j softplus(b_k x_j) - softplus(b_{k-1} x_j) and the draw h ~ sigma(b_k x);
+// then v ~ sigma(a + b_k h W^T).  logw[b] (nats) is written for this shard's chains.
+int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n_betas, uint64_t seed,
+                 uint64_t chain_offset, double* logw, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const Plan pl = make_plan(p->n_visible, p->n_hidden, M);
+  RBM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, RBM_B200_ERR_WORKSPACE,
+              "AIS needs %zu bytes of workspace, got %zu", pl.total, ws_bytes);
+  int dev = 0, sm_count = 0, cc_major = 0;
+  RBM_CUDA_TRY(cudaGetDevice(&dev));
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  RBM_REQUIRE(cc_major == 10, RBM_B200_ERR_NO_DEVICE, "AIS needs an sm_100 device (got cc %d.x)", cc_major);
+
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  uint16_t* Wp = reinterpret_cast<uint16_t*>(base + pl.off_W);
+  float* nbh = reinterpret_cast<float*>(base + pl.off_nbh);
+  float* nbv = reinterpret_cast<float*>(base + pl.off_nbv);
+  __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(base + pl.off_V);
+  __nv_bfloat16* Hs = reinterpret_cast<__nv_bfloat16*>(base + pl.off_H);
+  float* wpart = reinterpret_cast<float*>(base + pl.off_wpart);
+
+  {
+    const int64_t n = (int64_t)pl.nVp * pl.nHp;
+    pad_w_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W_bf16, Wp, pl.nV, pl.nH, pl.nVp, pl.nHp);
+    const int nh256 = round_up(pl.nHp, 256), nv256 = round_up(pl.nVp, 256);
+    nbias_kernel<<<ceil_div(nh256, 256), 256, 0, st>>>(p->hbias, nbh, pl.nH, nh256);
+    nbias_kernel<<<ceil_div(nv256, 256), 256, 0, st>>>(p->vbias, nbv, pl.nV, nv256);
+    RBM_CUDA_TRY(cudaMemsetAsync(wpart, 0, (size_t)pl.rows_pad * pl.wpart_ld * 4, st));
+    const int64_t nb = pl.rows_pad * (pl.nVp / 8);
+    ais_init_kernel<<<(unsigned)ceil_div64(nb, 256), 256, 0, st>>>(Vs, pl.rows_pad, pl.nV, pl.nVp, nbv,
+                                                                  make_draw_ctx(seed, 0, TAG_AIS_INIT), chain_offset);
+  }
+  int rc = check_launch("ais staging kernels");
+  if (rc) return rc;
+
+  CUtensorMap tm_v, tm_h, tm_w_mn, tm_w_k;
+  if ((rc = make_tmap(&tm_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
+  if ((rc = make_tmap(&tm_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
+  if ((rc = make_tmap(&tm_w_mn, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&tm_w_k, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, (uint32_t)pl.bn_v))) return rc;
+
+  HalfStepArgs ah{}, av{};
+  ah.out = Hs; ah.nbias = nbh; ah.ldo = pl.nHp; ah.m_tiles = (int)(pl.rows_pad / BLOCK_M);
+  ah.n_tiles = ceil_div(pl.nHp, pl.bn_h); ah.k_blocks = pl.nVp / BLOCK_K; ah.chain_offset = chain_offset;
+  ah.n_valid = pl.nH; ah.wpart = wpart; ah.wpart_ld = pl.wpart_ld;
+  av.out = Vs; av.nbias = nbv; av.ldo = pl.nVp; av.m_tiles = ah.m_tiles;
+  av.n_tiles = ceil_div(pl.nVp, pl.bn_v); av.k_blocks = pl.nHp / BLOCK_K; av.chain_offset = chain_offset;
+  av.n_valid = pl.nV; av.wpart = wpart; av.wpart_ld = pl.wpart_ld;
+
+  const int K = n_betas - 1;
+  for (int k = 1; k <= K; ++k) {
+    const float bk = (float)betas[k], bkm1 = (float)betas[k - 1];
+    ah.ctx = make_draw_ctx(seed, 2ull * k, TAG_AIS);
+    ah.scale = -1.4426950408889634f * bk; ah.bmul = bk; ah.ratio = bkm1 / bk;
+    rc = pl.bn_h == 256 ? launch_half_step<256, true, EPI_AIS_WEIGHT>(tm_v, tm_w_mn, ah, sm_count, st)
+                        : launch_half_step<128, true, EPI_AIS_WEIGHT>(tm_v, tm_w_mn, ah, sm_count, st);
+    if (rc) return rc;
+    if (k == K) break;  // the last transition cannot change the estimate
+    av.ctx = make_draw_ctx(seed, 2ull * k + 1, TAG_AIS);
+    av.scale = -1.4426950408889634f * bk; av.bmul = 1.0f; av.ratio = 0.f;
+    rc = pl.bn_v == 256 ? launch_half_step<256, false, EPI_ANNEALED>(tm_h, tm_w_k, av, sm_count, st)
+                        : launch_half_step<128, false, EPI_ANNEALED>(tm_h, tm_w_k, av, sm_count, st);
+    if (rc) return rc;
+  }
+  ais_reduce_kernel<<<(unsigned)ceil_div64(M, 256), 256, 0, st>>>(wpart, pl.wpart_ld, M, logw);
+  return check_launch("ais_reduce_kernel");
 }
 
 }  // namespace rbm

@@ -33,4 +33,8 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
                      uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws,
                      size_t ws_bytes, cudaStream_t st);
 
+size_t umma_ais_workspace_bytes(int nV, int nH, int64_t M);
+int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n_betas, uint64_t seed,
+                 uint64_t chain_offset, double* logw, void* ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace rbm

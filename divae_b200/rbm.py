@@ -59,6 +59,45 @@ class RBM(nn.Module):
             return self._logZ
         return 33.65
 
+    def estimate_logZ(self, n_chains=16384, n_betas=10000, seed=0x5EED, betas=None, group=None, return_logw=False):
+        """Annealed-importance-sampling estimate of log Z (new capability; the reference hard-codes
+        33.65, rbm.py:51-54).  Chains shard over the ranks of `group` (or the default process group
+        when torch.distributed is initialised): every rank runs n_chains / world_size chains keyed by
+        their global chain id and the log-weights are combined with an NCCL log-sum-exp.
+        Stores the estimate so that get_logZ_value() / log_prob() use it.  Algorithm: include/rbm_b200.h
+        (rbm_b200_ais_run), CPU restatement: oracle/rbm_oracle.py:ais_logZ."""
+        import ctypes
+        import math
+        import numpy as np
+        import torch.distributed as tdist
+        from . import _lib, dist as _dist
+        lib = _lib.load()
+        _lib.require_cuda(self._weights, "RBM parameters")
+        dev = self._weights.device
+        rank, world = 0, 1
+        if tdist.is_available() and tdist.is_initialized():
+            rank, world = tdist.get_rank(group), tdist.get_world_size(group)
+        offset, n_local = _dist.shard_chains(n_chains, rank, world)
+        if betas is None:
+            betas = np.linspace(0.0, 1.0, int(n_betas) + 1)
+        betas = np.ascontiguousarray(betas, dtype=np.float64)
+        p, keep = self._pack.pack(self, need_bf16=True)
+        logw = torch.empty(n_local, dtype=torch.float64, device=dev)
+        nbytes = lib.rbm_b200_ais_workspace(p.n_visible, p.n_hidden, n_local)
+        ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dev)
+        with torch.no_grad(), torch.cuda.device(dev):
+            _lib.check(lib.rbm_b200_ais_run(ctypes.byref(p), n_local, betas.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                            len(betas), int(seed) & 0xFFFFFFFFFFFFFFFF, offset, _ops._ptr(logw),
+                                            _ops._ptr(ws), nbytes, _ops._stream()), "ais_run")
+            lse = _dist.logsumexp_allreduce(logw, group=group)
+            a = self._visible_bias.detach().double()
+            logZA = p.n_hidden * math.log(2.0) + torch.nn.functional.softplus(a).sum()
+            logZ = float((logZA + lse - math.log(n_chains)).item())
+        self._logZ = logZ
+        if return_logw:
+            return logZ, logw
+        return logZ
+
     def energy(self, post_samples):
         """Energy of samples, vis*b_vis + hid*b_hid + vis*w*hid (rbm.py:56-72).
 

@@ -153,6 +153,23 @@ RBM_B200_API int rbm_b200_negative_phase(const float *v, const float *h, int64_t
                             int32_t n_hidden, float scale, float *S_vh, float *S_v, float *S_h,
                             void *stream);
 
+/* Annealed importance sampling of log Z (Salakhutdinov & Murray 2008, RBM form).  The
+ * reference has NO estimator: RBM.get_logZ_value returns the literal 33.65
+ * (models/rbm/rbm.py:51-54); this entry supplies the missing computation.
+ * Base-rate model A = (W = 0, c = 0, visible bias a).  For chain b of this shard:
+ *   v ~ p_A;  for k = 1..K:  logw[b] += sum_j softplus(beta_k x_j) - softplus(beta_{k-1} x_j),
+ *   x = v W + c;  h ~ sigma(beta_k x);  v ~ sigma(a + beta_k h W^T)
+ * and  log Z = n_hidden*log 2 + sum_i softplus(a_i) + logsumexp_b(logw) - log(total chains),
+ * the logsumexp running over all shards (NCCL on the caller's side).
+ *   betas   HOST pointer, n_betas doubles, betas[0] = 0 < ... < betas[n_betas-1] = 1.
+ *   logw    DEVICE pointer, n_chains doubles (nats), overwritten.
+ *   chain_offset  global id of this shard's first chain (draws are keyed by global id).
+ * Needs W_bf16 and rbm_b200_ais_workspace(...) bytes of workspace. */
+RBM_B200_API size_t rbm_b200_ais_workspace(int32_t n_visible, int32_t n_hidden, int64_t n_chains);
+RBM_B200_API int rbm_b200_ais_run(const rbm_b200_params *p, int64_t n_chains, const double *betas,
+                                  int32_t n_betas, uint64_t seed, uint64_t chain_offset, double *logw,
+                                  void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,84 @@
+"""GPU AIS log Z (rbm_b200_ais_run through RBM.estimate_logZ): within 0.05 nats of exact
+enumeration and of the CPU restatement (oracle/rbm_oracle.py:ais_logZ) — north-star tolerance."""
+import numpy as np
+import pytest
+import torch
+
+import divae_b200
+from oracle import rbm_oracle as orc
+from test_gpu_umma import make_rbm
+
+pytestmark = pytest.mark.gpu
+
+
+def small_rbm(nV, nH, scale, seed):
+    rng = np.random.default_rng(seed)
+    W = orc.round_bf16((rng.standard_normal((nV, nH)) * scale).astype(np.float32))
+    a = (0.3 * rng.standard_normal(nV)).astype(np.float32)
+    c = (0.3 * rng.standard_normal(nH)).astype(np.float32)
+    return W, a, c
+
+
+@pytest.mark.parametrize("nV,nH,scale", [(12, 10, 0.5), (14, 14, 0.4), (40, 16, 0.25)])
+def test_ais_matches_exact_enumeration(nV, nH, scale):
+    W, a, c = small_rbm(nV, nH, scale, nV)
+    exact = orc.exact_logZ(W, a, c)
+    rbm = make_rbm(W, a, c)
+    est = rbm.estimate_logZ(n_chains=2048, n_betas=1000, seed=7)
+    assert abs(est - exact) < 0.05, (est, exact)
+    assert rbm.get_logZ_value() == est                   # replaces the 33.65 placeholder (rbm.py:54)
+    v, h = torch.ones(2, nV, device="cuda:0"), torch.zeros(2, nH, device="cuda:0")
+    if nV == nH:
+        torch.testing.assert_close(rbm.log_prob([v, h]), -rbm.energy([v, h]) - est)
+    else:   # the reference splits the concatenation in halves (rbm.py:61-63): ragged priors cannot be scored
+        with pytest.raises(RuntimeError, match="size mismatch"):
+            rbm.log_prob([v, h])
+
+
+def test_ais_tracks_cpu_restatement_chain_by_chain():
+    W, a, c = small_rbm(64, 48, 0.15, 3)
+    rbm = make_rbm(W, a, c)
+    M, K = 256, 200
+    est, logw = rbm.estimate_logZ(n_chains=M, n_betas=K, seed=11, return_logw=True)
+    ref, ref_logw, _ = orc.ais_logZ(W, a, c, M, np.linspace(0, 1, K + 1), 11, return_logw=True)
+    assert abs(est - ref) < 0.05, (est, ref)
+    # chains that never meet a near-threshold draw follow the oracle's trajectory exactly
+    diff = np.abs(logw.cpu().numpy() - ref_logw)
+    assert np.median(diff) < 5e-3 and (diff < 5e-2).mean() > 0.8
+
+
+def test_ais_config5_shape_against_cpu_restatement():
+    """BASELINE config 5 prior (2 x 512) with a reduced schedule; weights at trained-like scale."""
+    W, a, c = small_rbm(512, 512, 0.02, 5)
+    rbm = make_rbm(W, a, c)
+    M, K = 256, 100
+    est = rbm.estimate_logZ(n_chains=M, n_betas=K, seed=2)
+    ref = orc.ais_logZ(W, a, c, M, np.linspace(0, 1, K + 1), 2)
+    assert abs(est - ref) < 0.05, (est, ref)
+
+
+def test_ais_sharding_by_chain_offset_is_exact():
+    import ctypes
+    from divae_b200 import _lib, _ops
+    W, a, c = small_rbm(96, 64, 0.2, 9)
+    rbm = make_rbm(W, a, c)
+    _, full = rbm.estimate_logZ(n_chains=300, n_betas=50, seed=4, return_logw=True)
+    lib = _lib.load()
+    p, keep = rbm._pack.pack(rbm, need_bf16=True)
+    betas = np.linspace(0, 1, 51)
+    part = torch.empty(100, dtype=torch.float64, device="cuda:0")
+    nbytes = lib.rbm_b200_ais_workspace(96, 64, 100)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda:0")
+    _lib.check(lib.rbm_b200_ais_run(ctypes.byref(p), 100, betas.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 51, 4, 150,
+                                    _ops._ptr(part), _ops._ptr(ws), nbytes, _ops._stream()))
+    torch.testing.assert_close(part, full[150:250], rtol=0, atol=1e-9)
+
+
+def test_ais_rejects_bad_schedules():
+    import ctypes
+    from divae_b200 import _lib
+    lib = _lib.load()
+    p = _lib.RbmParams(8, 8, 1, 1, 1, 1)
+    bad = np.array([0.0, 0.5, 0.4, 1.0])
+    rc = lib.rbm_b200_ais_run(ctypes.byref(p), 4, bad.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 4, 0, 0, 1, 1, 0, None)
+    assert rc == _lib.ERR_INVALID and b"increasing" in lib.rbm_b200_last_error()
