@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -34,6 +35,7 @@ constexpr int kStages = 4;
 constexpr int kNumEpilogueWarps = 16;  // 4 per TMEM lane quarter; each owns BLOCK_N/4 columns
 constexpr int kNumThreads = 128 + kNumEpilogueWarps * 32;
 constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int kStoreWarpBytes = 32 * 32 * 2;    // one [32 chains x 32 units] bf16 box per epilogue warp (SWIZZLE_64B)
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,6 +66,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -129,7 +142,9 @@ template <int BLOCK_N>
 struct SmemLayout {
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kStoreOffset = kStages * kStageBytes;             // epilogue -> TMA-store staging
+  static constexpr int kStoreBytes = kNumEpilogueWarps * kStoreWarpBytes;
+  static constexpr int kBarOffset = kStoreOffset + kStoreBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers/tmem ptr + alignment slack
 };
 
@@ -148,6 +163,7 @@ struct HalfStepArgs {
   float ratio;             // beta_{k-1} / beta_k
   float* wpart;            // [rows_pad, wpart_ld] running log-weight partials (log2 units)
   int wpart_ld;
+  int debug_mode;          // profiling only (env RBM_B200_DEBUG_MODE): 1 = skip epilogue math, 2 = skip TMA+MMA
 };
 
 // Epilogue flavours
@@ -192,7 +208,7 @@ __device__ __noinline__ uint32_t resolve_exact(float arg, uint32_t k16, DrawCtx 
 template <int BLOCK_N, bool B_MN_MAJOR, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                      const HalfStepArgs args) {
+                      const __grid_constant__ CUtensorMap tmap_out, const HalfStepArgs args) {
   using L = SmemLayout<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -214,6 +230,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   if (warp_idx == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -232,7 +249,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   if (warp_idx == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    if (lane == 0 && args.debug_mode != 2) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_blk = tile % args.n_tiles, m_blk = tile / args.n_tiles;
@@ -266,7 +283,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         mbar_wait(tmem_empty_bar(as), (((uint32_t)it >> 1) & 1u) ^ 1u);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
-        for (int kb = 0; kb < args.k_blocks; ++kb) {
+        for (int kb = 0; kb < (args.debug_mode == 2 ? 0 : args.k_blocks); ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * L::kStageBytes;
@@ -290,6 +307,10 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const int cq = (warp_idx - 4) >> 2;          // which quarter of the tile's columns
     constexpr int kColsPerWarp = BLOCK_N / 4;
     constexpr int kGroups = kColsPerWarp / 32;   // 32-unit Philox groups per warp per tile
+    // staging box of this warp: row `lane` = 64 B, 16-B chunk c stored at c ^ ((lane >> 1) & 3)  (SWIZZLE_64B)
+    const uint32_t stage_warp = smem_base + L::kStoreOffset + (uint32_t)(warp_idx - 4) * kStoreWarpBytes;
+    const uint32_t stage_row = stage_warp + (uint32_t)lane * 64u;
+    const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int n_blk = tile % args.n_tiles, m_blk = tile / args.n_tiles;
@@ -298,7 +319,6 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       tcgen05_fence_after();
       const int row = m_blk * BLOCK_M + quarter * 32 + lane;
       const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)row);
-      __nv_bfloat16* out_row = args.out + (size_t)row * args.ldo;
       float wsum = 0.f;   // EPI_AIS_WEIGHT: this thread's log-weight increment over its columns (log2 units)
 #pragma unroll 1
       for (int g = 0; g < kGroups; ++g) {
@@ -306,6 +326,11 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int col0 = n_blk * BLOCK_N + col_in_tile;
         const bool live = col0 < args.ldo;   // tile overhang beyond the padded unit count
         const uint32_t blk0 = (uint32_t)(col0 >> 5) * 4u;
+        if (live) {
+          // the previous TMA store of this warp must have finished READING the staging box
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
         // four Philox calls cover the 32 units of this group (slot mapping: philox.cuh)
         uint32_t w[4][4];
 #pragma unroll
@@ -324,7 +349,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(as));
           }
-          if (!live) continue;
+          if (!live || args.debug_mode == 1) continue;
           uint32_t pk[8];       // 16 units -> 16 bf16 {0,1}, packed in pairs
           bool amb = false;
 #pragma unroll
@@ -374,9 +399,19 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               if (c16 & 1) pk[c16 >> 1] |= val; else pk[c16 >> 1] = val;
             }
           }
-          uint4* dst = reinterpret_cast<uint4*>(out_row + col0 + 16 * hh);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          // 16 units = 32 B = two 16-B chunks of this chain's row in the staging box
+          st_shared_v4(stage_row + (((uint32_t)(2 * hh) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(stage_row + (((uint32_t)(2 * hh + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+        }
+        if (live && args.debug_mode != 1) {
+          // generic-proxy writes -> visible to the async proxy, then ONE coalesced TMA store of the
+          // [32 chains x 32 units] box; columns beyond the padded unit count are clipped by TMA
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, stage_warp, col0, m_blk * BLOCK_M + quarter * 32);
+            tma_store_commit();
+          }
         }
       }
       if (EPI == EPI_AIS_WEIGHT) {
@@ -385,6 +420,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         *slot_ptr += wsum;
       }
     }
+    if (lane == 0) tma_store_wait_all();   // state tiles must be complete before the kernel ends
   }
 
   tcgen05_fence_before();
@@ -489,16 +525,17 @@ int get_encode_fn(EncodeTiledFn* out) {
 }
 
 // bf16 row-major [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128B swizzle
-int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+              uint32_t box_cols = 64, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn;
   int rc = get_encode_fn(&fn);
   if (rc) return rc;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RBM_REQUIRE(r == CUDA_SUCCESS, RBM_B200_ERR_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
@@ -538,7 +575,8 @@ Plan make_plan(int nV, int nH, int64_t B) {
 }
 
 template <int BLOCK_N, bool B_MN_MAJOR, int EPI = EPI_GIBBS>
-int launch_half_step(const CUtensorMap& ta, const CUtensorMap& tb, const HalfStepArgs& a, int sm_count, cudaStream_t st) {
+int launch_half_step(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HalfStepArgs& a,
+                     int sm_count, cudaStream_t st) {
   auto kern = umma_half_step_kernel<BLOCK_N, B_MN_MAJOR, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -546,7 +584,10 @@ int launch_half_step(const CUtensorMap& ta, const CUtensorMap& tb, const HalfSte
     configured = true;
   }
   const int grid = std::min(a.m_tiles * a.n_tiles, sm_count);
-  kern<<<grid, kNumThreads, SmemLayout<BLOCK_N>::kTotal, st>>>(ta, tb, a);
+  static const int debug_mode = [] { const char* e = getenv("RBM_B200_DEBUG_MODE"); return e ? atoi(e) : 0; }();
+  HalfStepArgs a2 = a;
+  a2.debug_mode = debug_mode;
+  kern<<<grid, kNumThreads, SmemLayout<BLOCK_N>::kTotal, st>>>(ta, tb, to, a2);
   return check_launch("umma_half_step_kernel");
 }
 
@@ -601,6 +642,10 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   if ((rc = make_tmap(&tm_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
   if ((rc = make_tmap(&tm_w_mn, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
   if ((rc = make_tmap(&tm_w_k, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, (uint32_t)pl.bn_v))) return rc;
+  // epilogue stores: [32 chains x 32 units] boxes, 64-byte swizzle
+  CUtensorMap to_v, to_h;
+  if ((rc = make_tmap(&to_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_tmap(&to_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
 
   HalfStepArgs ah{}, av{};
   ah.out = Hs; ah.nbias = nbh; ah.ldo = pl.nHp; ah.m_tiles = (int)(pl.rows_pad / BLOCK_M);
@@ -610,12 +655,12 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
 
   for (int s = 0; s < k; ++s) {
     ah.ctx = make_draw_ctx(seed, step_offset + 2ull * s, TAG_GIBBS);
-    rc = pl.bn_h == 256 ? launch_half_step<256, true>(tm_v, tm_w_mn, ah, sm_count, st)
-                        : launch_half_step<128, true>(tm_v, tm_w_mn, ah, sm_count, st);
+    rc = pl.bn_h == 256 ? launch_half_step<256, true>(tm_v, tm_w_mn, to_h, ah, sm_count, st)
+                        : launch_half_step<128, true>(tm_v, tm_w_mn, to_h, ah, sm_count, st);
     if (rc) return rc;
     av.ctx = make_draw_ctx(seed, step_offset + 2ull * s + 1, TAG_GIBBS);
-    rc = pl.bn_v == 256 ? launch_half_step<256, false>(tm_h, tm_w_k, av, sm_count, st)
-                        : launch_half_step<128, false>(tm_h, tm_w_k, av, sm_count, st);
+    rc = pl.bn_v == 256 ? launch_half_step<256, false>(tm_h, tm_w_k, to_v, av, sm_count, st)
+                        : launch_half_step<128, false>(tm_h, tm_w_k, to_v, av, sm_count, st);
     if (rc) return rc;
   }
   // back to the reference's dtype
@@ -672,6 +717,10 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
   if ((rc = make_tmap(&tm_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
   if ((rc = make_tmap(&tm_w_mn, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
   if ((rc = make_tmap(&tm_w_k, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, (uint32_t)pl.bn_v))) return rc;
+  // epilogue stores: [32 chains x 32 units] boxes, 64-byte swizzle
+  CUtensorMap to_v, to_h;
+  if ((rc = make_tmap(&to_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_tmap(&to_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
 
   HalfStepArgs ah{}, av{};
   ah.out = Hs; ah.nbias = nbh; ah.ldo = pl.nHp; ah.m_tiles = (int)(pl.rows_pad / BLOCK_M);
@@ -686,14 +735,14 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
     const float bk = (float)betas[k], bkm1 = (float)betas[k - 1];
     ah.ctx = make_draw_ctx(seed, 2ull * k, TAG_AIS);
     ah.scale = -1.4426950408889634f * bk; ah.bmul = bk; ah.ratio = bkm1 / bk;
-    rc = pl.bn_h == 256 ? launch_half_step<256, true, EPI_AIS_WEIGHT>(tm_v, tm_w_mn, ah, sm_count, st)
-                        : launch_half_step<128, true, EPI_AIS_WEIGHT>(tm_v, tm_w_mn, ah, sm_count, st);
+    rc = pl.bn_h == 256 ? launch_half_step<256, true, EPI_AIS_WEIGHT>(tm_v, tm_w_mn, to_h, ah, sm_count, st)
+                        : launch_half_step<128, true, EPI_AIS_WEIGHT>(tm_v, tm_w_mn, to_h, ah, sm_count, st);
     if (rc) return rc;
     if (k == K) break;  // the last transition cannot change the estimate
     av.ctx = make_draw_ctx(seed, 2ull * k + 1, TAG_AIS);
     av.scale = -1.4426950408889634f * bk; av.bmul = 1.0f; av.ratio = 0.f;
-    rc = pl.bn_v == 256 ? launch_half_step<256, false, EPI_ANNEALED>(tm_h, tm_w_k, av, sm_count, st)
-                        : launch_half_step<128, false, EPI_ANNEALED>(tm_h, tm_w_k, av, sm_count, st);
+    rc = pl.bn_v == 256 ? launch_half_step<256, false, EPI_ANNEALED>(tm_h, tm_w_k, to_v, av, sm_count, st)
+                        : launch_half_step<128, false, EPI_ANNEALED>(tm_h, tm_w_k, to_v, av, sm_count, st);
     if (rc) return rc;
   }
   ais_reduce_kernel<<<(unsigned)ceil_div64(M, 256), 256, 0, st>>>(wpart, pl.wpart_ld, M, logw);
