@@ -31,7 +31,6 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // one 128-byte swizzle atom of bf16 along K
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
 constexpr int kNumEpilogueWarps = 16;  // 4 per TMEM lane quarter; each owns BLOCK_N/4 columns
 constexpr int kNumThreads = 128 + kNumEpilogueWarps * 32;
 constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
@@ -77,6 +76,45 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// ---- cluster-pair (cta_group::2) flavours
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -138,9 +176,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major)
          | ((uint32_t)(M >> 4) << 24);   // m_dim
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CTAS>
 struct SmemLayout {
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  // CTAS = 2: the two CTAs of a cluster pair each hold HALF of the B (W) tile; 32 KB stages
+  static constexpr int kStages = CTAS == 2 ? 5 : 4;
+  static constexpr int kBBytes = (BLOCK_N / CTAS) * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStoreOffset = kStages * kStageBytes;             // epilogue -> TMA-store staging
   static constexpr int kStoreBytes = kNumEpilogueWarps * kStoreWarpBytes;
@@ -205,13 +245,15 @@ __device__ __noinline__ uint32_t resolve_exact(float arg, uint32_t k16, DrawCtx 
   return ((y - fl) * 65536.0f >= (float)e16) ? 1u : 0u;
 }
 
-template <int BLOCK_N, bool B_MN_MAJOR, int EPI>
+template <int BLOCK_N, bool B_MN_MAJOR, int EPI, int CTAS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const HalfStepArgs args) {
-  using L = SmemLayout<BLOCK_N>;
+  using L = SmemLayout<BLOCK_N, CTAS>;
+  constexpr int kStages = L::kStages;
+  constexpr int kBCols = BLOCK_N / CTAS;        // columns of the B tile this CTA stages
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
+  // SWIZZLE_128B tiles need 1024-byte alignment (same offset in both CTAs of a pair)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + L::kBarOffset;
@@ -224,7 +266,12 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = args.m_tiles * args.n_tiles;
+  // CTAS = 2: CTA pair (cluster of 2) works on a 256-chain x BLOCK_N tile; rank 0 is the leader that
+  // issues the MMAs; the full/tmem_empty barriers that gate the MMAs live in the leader.
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int num_tiles = (args.m_tiles / CTAS) * args.n_tiles;     // m_tiles counts 128-chain tiles
+  const int first_tile = (int)blockIdx.x / CTAS, tile_stride = (int)gridDim.x / CTAS;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 or 512)
 
   if (warp_idx == 0 && lane == 0) {
@@ -233,17 +280,23 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
   }
   if (warp_idx == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), kNumEpilogueWarps); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), CTAS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), kNumEpilogueWarps * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp_idx == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -251,22 +304,39 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     // =============================== TMA producer ===============================
     if (lane == 0 && args.debug_mode != 2) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const int n_blk = tile % args.n_tiles, m_blk = tile / args.n_tiles;
+        const int row0 = (m_blk * CTAS + (int)cta_rank) * BLOCK_M;          // this CTA's 128 chains
+        const int ncol0 = n_blk * BLOCK_N + (int)cta_rank * kBCols;         // this CTA's share of the W tile
         for (int kb = 0; kb < args.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * L::kStageBytes;
           const uint32_t sb = sa + kABytes;
-          mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
-          if (B_MN_MAJOR) {
-            // W[k rows][n cols]: one [64 x 64] box per 64-column MN block, 8 KB apart (LBO)
+          if (CTAS == 1) {
+            mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, row0);
+            if (B_MN_MAJOR) {
+              // W[k rows][n cols]: one [64 x 64] box per 64-column MN block, 8 KB apart (LBO)
 #pragma unroll
-            for (int nb = 0; nb < BLOCK_N / 64; ++nb)
-              tma_load_2d(sb + nb * (BLOCK_K * 128), &tmap_b, full_bar(stage), n_blk * BLOCK_N + nb * 64, kb * BLOCK_K);
+              for (int nb = 0; nb < kBCols / 64; ++nb)
+                tma_load_2d(sb + nb * (BLOCK_K * 128), &tmap_b, full_bar(stage), ncol0 + nb * 64, kb * BLOCK_K);
+            } else {
+              // W[n rows][k cols]: one [kBCols x 64] box, rows of 128 B
+              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BLOCK_K, ncol0);
+            }
           } else {
-            // W[n rows][k cols]: one [BLOCK_N x 64] box, rows of 128 B
-            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+            // both CTAs credit the LEADER's full barrier (2 arrivals + the bytes of both CTAs)
+            const uint32_t lead_full = mapa_u32(full_bar(stage), 0);
+            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * L::kStageBytes);
+            else mbar_arrive_cluster(lead_full);
+            tma_load_2d_pair(sa, &tmap_a, lead_full, kb * BLOCK_K, row0);
+            if (B_MN_MAJOR) {
+#pragma unroll
+              for (int nb = 0; nb < kBCols / 64; ++nb)
+                tma_load_2d_pair(sb + nb * (BLOCK_K * 128), &tmap_b, lead_full, ncol0 + nb * 64, kb * BLOCK_K);
+            } else {
+              tma_load_2d_pair(sb, &tmap_b, lead_full, kb * BLOCK_K, ncol0);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -274,11 +344,11 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
   } else if (warp_idx == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, B_MN_MAJOR);
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M * CTAS, BLOCK_N, B_MN_MAJOR);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
         const int as = it & 1;
         mbar_wait(tmem_empty_bar(as), (((uint32_t)it >> 1) & 1u) ^ 1u);
         tcgen05_fence_after();
@@ -293,12 +363,15 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint64_t adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
             const uint64_t bdesc = B_MN_MAJOR ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                               : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CTAS == 2) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (CTAS == 2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tmem_full_bar(as));   // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CTAS == 2) umma_commit_pair(tmem_full_bar(as)); else umma_commit(tmem_full_bar(as));
       }
     }
   } else if (warp_idx >= 4) {
@@ -312,12 +385,13 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const uint32_t stage_row = stage_warp + (uint32_t)lane * 64u;
     const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
       const int n_blk = tile % args.n_tiles, m_blk = tile / args.n_tiles;
       const int as = it & 1;
       mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u);
       tcgen05_fence_after();
-      const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+      const int row_base = (m_blk * CTAS + (int)cta_rank) * BLOCK_M + quarter * 32;
+      const int row = row_base + lane;
       const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)row);
       float wsum = 0.f;   // EPI_AIS_WEIGHT: this thread's log-weight increment over its columns (log2 units)
 #pragma unroll 1
@@ -347,7 +421,10 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             // all of this warp's TMEM reads for the tile are done: hand the stage back
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(as));
+            if (lane == 0) {
+              if (CTAS == 2) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(as), 0));   // the leader's barrier
+              else mbar_arrive(tmem_empty_bar(as));
+            }
           }
           if (!live || args.debug_mode == 1) continue;
           uint32_t pk[8];       // 16 units -> 16 bf16 {0,1}, packed in pairs
@@ -409,7 +486,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmap_out, stage_warp, col0, m_blk * BLOCK_M + quarter * 32);
+            tma_store_2d(&tmap_out, stage_warp, col0, row_base);
             tma_store_commit();
           }
         }
@@ -423,11 +500,15 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (lane == 0) tma_store_wait_all();   // state tiles must be complete before the kernel ends
   }
 
+  __syncwarp();   // re-converge the single-lane roles before the block / cluster barrier
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp_idx == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -541,9 +622,15 @@ int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, 
   return 0;
 }
 
+// CTA pairs (tcgen05 cta_group::2) are the default for 256-wide tiles; RBM_B200_PAIRS=0 forces single CTAs
+bool pairs_enabled() {
+  static const bool on = [] { const char* e = getenv("RBM_B200_PAIRS"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
 struct Plan {
   int nV, nH, nVp, nHp;      // padded to multiples of 64
-  int64_t rows_pad;          // chains padded to a multiple of 128
+  int64_t rows_pad;          // chains padded to a multiple of 256 (one CTA-pair tile)
   int bn_h, bn_v;            // BLOCK_N for the v->h and h->v half-steps
   size_t off_W, off_nbh, off_nbv, off_V, off_H, off_wpart, total;
   int wpart_ld;              // AIS log-weight partial slots per chain: 4 per hidden-side N tile
@@ -559,7 +646,7 @@ Plan make_plan(int nV, int nH, int64_t B) {
   Plan p;
   p.nV = nV; p.nH = nH;
   p.nVp = round_up(nV, 64); p.nHp = round_up(nH, 64);
-  p.rows_pad = ceil_div64(B, BLOCK_M) * BLOCK_M;
+  p.rows_pad = ceil_div64(B, 2 * BLOCK_M) * (2 * BLOCK_M);   // whole CTA-pair tiles (256 chains)
   p.bn_h = pick_block_n(p.nHp); p.bn_v = pick_block_n(p.nVp);
   auto align = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
   size_t o = 0;
@@ -574,21 +661,44 @@ Plan make_plan(int nV, int nH, int64_t B) {
   return p;
 }
 
-template <int BLOCK_N, bool B_MN_MAJOR, int EPI = EPI_GIBBS>
-int launch_half_step(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HalfStepArgs& a,
-                     int sm_count, cudaStream_t st) {
-  auto kern = umma_half_step_kernel<BLOCK_N, B_MN_MAJOR, EPI>;
+template <int BLOCK_N, bool B_MN_MAJOR, int EPI, int CTAS>
+int launch_half_step_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HalfStepArgs& a,
+                          int sm_count, cudaStream_t st) {
+  auto kern = umma_half_step_kernel<BLOCK_N, B_MN_MAJOR, EPI, CTAS>;
+  using L = SmemLayout<BLOCK_N, CTAS>;
   static bool configured = false;
   if (!configured) {
-    RBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BLOCK_N>::kTotal));
+    RBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  const int grid = std::min(a.m_tiles * a.n_tiles, sm_count);
   static const int debug_mode = [] { const char* e = getenv("RBM_B200_DEBUG_MODE"); return e ? atoi(e) : 0; }();
   HalfStepArgs a2 = a;
   a2.debug_mode = debug_mode;
-  kern<<<grid, kNumThreads, SmemLayout<BLOCK_N>::kTotal, st>>>(ta, tb, to, a2);
+  const int tiles = (a.m_tiles / CTAS) * a.n_tiles;
+  const int grid = CTAS * std::min(tiles, sm_count / CTAS);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RBM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, a2));
   return check_launch("umma_half_step_kernel");
+}
+
+// use_pairs: CTA pairs (tcgen05 cta_group::2) when the tile is 256 wide.  Measured on B200 under the
+// 1 kW power cap (profiles/r01_pairs_vs_single.txt): ~4% faster than single CTAs on long persistent
+// loops (half the W traffic into shared memory), slower when a CTA only sees a few tiles.
+template <int BLOCK_N, bool B_MN_MAJOR, int EPI = EPI_GIBBS>
+int launch_half_step(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HalfStepArgs& a,
+                     int sm_count, bool use_pairs, cudaStream_t st) {
+  if (BLOCK_N == 256 && use_pairs)
+    return launch_half_step_impl<256, B_MN_MAJOR, EPI, 2>(ta, tb, to, a, sm_count, st);
+  return launch_half_step_impl<BLOCK_N, B_MN_MAJOR, EPI, 1>(ta, tb, to, a, sm_count, st);
 }
 
 }  // namespace
@@ -641,7 +751,11 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   if ((rc = make_tmap(&tm_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
   if ((rc = make_tmap(&tm_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
   if ((rc = make_tmap(&tm_w_mn, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
-  if ((rc = make_tmap(&tm_w_k, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, (uint32_t)pl.bn_v))) return rc;
+  // pairs pay off once every cluster loops over >= 8 tiles (profiles/r01_pairs_vs_single.txt)
+  const bool pairs = pairs_enabled() && (pl.rows_pad / (2 * BLOCK_M)) * ceil_div(std::max(pl.nVp, pl.nHp), 256) >= 8 * (sm_count / 2);
+  // h->v reads W K-major in [n rows x 64] boxes: a CTA of a pair stages half of the 256 rows
+  if ((rc = make_tmap(&tm_w_k, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp,
+                      (uint32_t)((pairs && pl.bn_v == 256) ? 128 : pl.bn_v)))) return rc;
   // epilogue stores: [32 chains x 32 units] boxes, 64-byte swizzle
   CUtensorMap to_v, to_h;
   if ((rc = make_tmap(&to_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
@@ -655,12 +769,12 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
 
   for (int s = 0; s < k; ++s) {
     ah.ctx = make_draw_ctx(seed, step_offset + 2ull * s, TAG_GIBBS);
-    rc = pl.bn_h == 256 ? launch_half_step<256, true>(tm_v, tm_w_mn, to_h, ah, sm_count, st)
-                        : launch_half_step<128, true>(tm_v, tm_w_mn, to_h, ah, sm_count, st);
+    rc = pl.bn_h == 256 ? launch_half_step<256, true>(tm_v, tm_w_mn, to_h, ah, sm_count, pairs, st)
+                        : launch_half_step<128, true>(tm_v, tm_w_mn, to_h, ah, sm_count, pairs, st);
     if (rc) return rc;
     av.ctx = make_draw_ctx(seed, step_offset + 2ull * s + 1, TAG_GIBBS);
-    rc = pl.bn_v == 256 ? launch_half_step<256, false>(tm_h, tm_w_k, to_v, av, sm_count, st)
-                        : launch_half_step<128, false>(tm_h, tm_w_k, to_v, av, sm_count, st);
+    rc = pl.bn_v == 256 ? launch_half_step<256, false>(tm_h, tm_w_k, to_v, av, sm_count, pairs, st)
+                        : launch_half_step<128, false>(tm_h, tm_w_k, to_v, av, sm_count, pairs, st);
     if (rc) return rc;
   }
   // back to the reference's dtype
@@ -716,7 +830,11 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
   if ((rc = make_tmap(&tm_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
   if ((rc = make_tmap(&tm_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
   if ((rc = make_tmap(&tm_w_mn, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
-  if ((rc = make_tmap(&tm_w_k, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, (uint32_t)pl.bn_v))) return rc;
+  // pairs pay off once every cluster loops over >= 8 tiles (profiles/r01_pairs_vs_single.txt)
+  const bool pairs = pairs_enabled() && (pl.rows_pad / (2 * BLOCK_M)) * ceil_div(std::max(pl.nVp, pl.nHp), 256) >= 8 * (sm_count / 2);
+  // h->v reads W K-major in [n rows x 64] boxes: a CTA of a pair stages half of the 256 rows
+  if ((rc = make_tmap(&tm_w_k, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp,
+                      (uint32_t)((pairs && pl.bn_v == 256) ? 128 : pl.bn_v)))) return rc;
   // epilogue stores: [32 chains x 32 units] boxes, 64-byte swizzle
   CUtensorMap to_v, to_h;
   if ((rc = make_tmap(&to_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
@@ -735,14 +853,14 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
     const float bk = (float)betas[k], bkm1 = (float)betas[k - 1];
     ah.ctx = make_draw_ctx(seed, 2ull * k, TAG_AIS);
     ah.scale = -1.4426950408889634f * bk; ah.bmul = bk; ah.ratio = bkm1 / bk;
-    rc = pl.bn_h == 256 ? launch_half_step<256, true, EPI_AIS_WEIGHT>(tm_v, tm_w_mn, to_h, ah, sm_count, st)
-                        : launch_half_step<128, true, EPI_AIS_WEIGHT>(tm_v, tm_w_mn, to_h, ah, sm_count, st);
+    rc = pl.bn_h == 256 ? launch_half_step<256, true, EPI_AIS_WEIGHT>(tm_v, tm_w_mn, to_h, ah, sm_count, pairs, st)
+                        : launch_half_step<128, true, EPI_AIS_WEIGHT>(tm_v, tm_w_mn, to_h, ah, sm_count, pairs, st);
     if (rc) return rc;
     if (k == K) break;  // the last transition cannot change the estimate
     av.ctx = make_draw_ctx(seed, 2ull * k + 1, TAG_AIS);
     av.scale = -1.4426950408889634f * bk; av.bmul = 1.0f; av.ratio = 0.f;
-    rc = pl.bn_v == 256 ? launch_half_step<256, false, EPI_ANNEALED>(tm_h, tm_w_k, to_v, av, sm_count, st)
-                        : launch_half_step<128, false, EPI_ANNEALED>(tm_h, tm_w_k, to_v, av, sm_count, st);
+    rc = pl.bn_v == 256 ? launch_half_step<256, false, EPI_ANNEALED>(tm_h, tm_w_k, to_v, av, sm_count, pairs, st)
+                        : launch_half_step<128, false, EPI_ANNEALED>(tm_h, tm_w_k, to_v, av, sm_count, pairs, st);
     if (rc) return rc;
   }
   ais_reduce_kernel<<<(unsigned)ceil_div64(M, 256), 256, 0, st>>>(wpart, pl.wpart_ld, M, logw);
