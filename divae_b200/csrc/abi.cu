@@ -41,10 +41,18 @@ static int require_device() {
   return 0;
 }
 
+// Shape-based kernel selection (one CUDA library, no backend dispatch).  Measured on B200
+// (profiles/r01_all_configs_1gpu.jsonl): the persistent shared-memory kernel wins for priors up to
+// 128 units per side at any chain count (64x64: 7.2e11 vs 3.0e11 unit-updates/s) and for up to
+// 256 units when chains are few (256x256 x 1024 chains: 0.20 ms vs 0.54 ms per call); with many
+// chains the tcgen05 GEMM wins at 256 units (6.9e11 vs 3.1e11).
 int pick_variant(const rbm_b200_params* p, int64_t B, int variant) {
   if (variant != RBM_B200_VARIANT_AUTO) return variant;
-  if (p->W_bf16 && smem_variant_supported(p->n_visible, p->n_hidden)) return RBM_B200_VARIANT_SMEM;
+  const int nmax = p->n_visible > p->n_hidden ? p->n_visible : p->n_hidden;
+  if (p->W_bf16 && smem_variant_supported(p->n_visible, p->n_hidden) && (nmax <= 128 || B < 8192))
+    return RBM_B200_VARIANT_SMEM;
   if (p->W_bf16 && umma_variant_supported(p->n_visible, p->n_hidden) && B >= 128) return RBM_B200_VARIANT_UMMA;
+  if (p->W_bf16 && smem_variant_supported(p->n_visible, p->n_hidden)) return RBM_B200_VARIANT_SMEM;
   return RBM_B200_VARIANT_GENERAL;
 }
 
