@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O3,-Wall,-fvisibility=hidden",
     "--expt-relaxed-constexpr",
     "-cudart", "static",
-]
+] + os.environ.get("RBM_B200_NVCC_DEFS", "").split()
 
 
 def _nvcc():

@@ -31,7 +31,11 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // one 128-byte swizzle atom of bf16 along K
 constexpr int UMMA_K = 16;
-constexpr int kNumEpilogueWarps = 16;  // 4 per TMEM lane quarter; each owns BLOCK_N/4 columns
+#ifndef RBM_EPI_WARPS
+#define RBM_EPI_WARPS 16
+#endif
+constexpr int kNumEpilogueWarps = RBM_EPI_WARPS;  // a multiple of 4: one set per TMEM lane quarter, columns split among sets
+constexpr int kEpiSets = kNumEpilogueWarps / 4;
 constexpr int kNumThreads = 128 + kNumEpilogueWarps * 32;
 constexpr int kABytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int kStoreWarpBytes = 32 * 32 * 2;    // one [32 chains x 32 units] bf16 box per epilogue warp (SWIZZLE_64B)
@@ -179,7 +183,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major)
 template <int BLOCK_N, int CTAS>
 struct SmemLayout {
   // CTAS = 2: the two CTAs of a cluster pair each hold HALF of the B (W) tile; 32 KB stages
-  static constexpr int kStages = CTAS == 2 ? 5 : 4;
+#ifndef RBM_PAIR_STAGES
+#define RBM_PAIR_STAGES 5
+#endif
+  static constexpr int kStages = CTAS == 2 ? RBM_PAIR_STAGES : 4;
   static constexpr int kBBytes = (BLOCK_N / CTAS) * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStoreOffset = kStages * kStageBytes;             // epilogue -> TMA-store staging
@@ -377,8 +384,8 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   } else if (warp_idx >= 4) {
     // ================================= epilogue =================================
     const int quarter = warp_idx & 3;            // TMEM lane quarter this warp may access
-    const int cq = (warp_idx - 4) >> 2;          // which quarter of the tile's columns
-    constexpr int kColsPerWarp = BLOCK_N / 4;
+    const int cq = (warp_idx - 4) >> 2;          // which share of the tile's columns
+    constexpr int kColsPerWarp = BLOCK_N / kEpiSets;
     constexpr int kGroups = kColsPerWarp / 32;   // 32-unit Philox groups per warp per tile
     // staging box of this warp: row `lane` = 64 B, 16-B chunk c stored at c ^ ((lane >> 1) & 3)  (SWIZZLE_64B)
     const uint32_t stage_warp = smem_base + L::kStoreOffset + (uint32_t)(warp_idx - 4) * kStoreWarpBytes;
@@ -493,7 +500,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       }
       if (EPI == EPI_AIS_WEIGHT) {
         // exactly one thread owns (row, slot) in a launch: plain read-modify-write, deterministic
-        float* slot_ptr = args.wpart + (size_t)row * args.wpart_ld + (n_blk * 4 + cq);
+        float* slot_ptr = args.wpart + (size_t)row * args.wpart_ld + (n_blk * kEpiSets + cq);
         *slot_ptr += wsum;
       }
     }
@@ -655,7 +662,7 @@ Plan make_plan(int nV, int nH, int64_t B) {
   p.off_nbv = o; o = align(o + (size_t)round_up(p.nVp, 256) * 4);
   p.off_V = o; o = align(o + (size_t)p.rows_pad * p.nVp * 2);
   p.off_H = o; o = align(o + (size_t)p.rows_pad * p.nHp * 2);
-  p.wpart_ld = 4 * ceil_div(p.nHp, p.bn_h);
+  p.wpart_ld = kEpiSets * ceil_div(p.nHp, p.bn_h);
   p.off_wpart = o; o = align(o + (size_t)p.rows_pad * p.wpart_ld * 4);
   p.total = o + 1024;  // slack to align the caller's pointer
   return p;
