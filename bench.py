@@ -82,7 +82,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        clocks, mx, reasons = [], [], set()
+        clocks, mx, reasons, power = [], [], set(), []
         try:
             with open(self.path) as f:
                 for line in f:
@@ -90,7 +90,7 @@ class ClockSampler:
                     if len(parts) < 9:
                         continue
                     try:
-                        clocks.append(float(parts[1])); mx.append(float(parts[2]))
+                        clocks.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
                     except ValueError:
                         continue
                     for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
@@ -102,7 +102,8 @@ class ClockSampler:
             pass
         if clocks:
             busy = sorted(clocks)[len(clocks) // 4:]  # drop idle samples at the edges
-            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(clocks))
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(clocks),
+                       power_w=statistics.median(sorted(power)[len(power) // 4:]) if power else None)
         return out
 
 
@@ -294,7 +295,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
-                   "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0)},
+                   "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0),
+                   "power_w": clocks.get("power_w")},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
                      "kernel": "umma_half_step_kernel", "flops_per_launch": flops_per_launch,
