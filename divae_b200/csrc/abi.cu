@@ -116,9 +116,11 @@ size_t rbm_b200_block_gibbs_workspace(int32_t n_visible, int32_t n_hidden, int64
   }
 }
 
-int rbm_b200_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int32_t k,
-                         int init_chains, uint64_t seed, uint64_t chain_offset, uint64_t step_offset,
-                         int variant, void* workspace, size_t workspace_bytes, void* stream) {
+static int block_gibbs_impl(const rbm_b200_params* p, float* v, float* h, int64_t B, int32_t k,
+                            int init_chains, uint64_t seed, uint64_t chain_offset, uint64_t step_offset,
+                            int variant, void* workspace, size_t workspace_bytes, void* stream, float* S_vh,
+                            float* S_v, float* S_h, bool* stats_fused) {
+  if (stats_fused) *stats_fused = false;
   int rc = check_params(p, false);
   if (rc) return rc;
   RBM_REQUIRE(B >= 0 && k >= 0, RBM_B200_ERR_INVALID, "negative batch or step count");
@@ -131,8 +133,10 @@ int rbm_b200_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B
   const int chosen = pick_variant(p, B, variant);
   if (chosen == RBM_B200_VARIANT_SMEM) {
     RBM_REQUIRE(p->W_bf16, RBM_B200_ERR_INVALID, "SMEM variant needs W_bf16");
+    const bool fuse = S_vh != nullptr && k > 0 && smem_can_fuse_stats(p->n_visible, p->n_hidden);
+    if (stats_fused) *stats_fused = fuse;
     return smem_block_gibbs(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, workspace,
-                            workspace_bytes, st);
+                            workspace_bytes, st, fuse ? S_vh : nullptr, fuse ? S_v : nullptr, fuse ? S_h : nullptr);
   }
   if (chosen == RBM_B200_VARIANT_UMMA) {
     RBM_REQUIRE(p->W_bf16, RBM_B200_ERR_INVALID, "UMMA variant needs W_bf16");
@@ -150,6 +154,31 @@ int rbm_b200_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B
                                 step_offset + 2ull * s + 1, TAG_GIBBS, st))) return rc;
   }
   return 0;
+}
+
+int rbm_b200_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int32_t k,
+                         int init_chains, uint64_t seed, uint64_t chain_offset, uint64_t step_offset,
+                         int variant, void* workspace, size_t workspace_bytes, void* stream) {
+  return block_gibbs_impl(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, variant, workspace,
+                          workspace_bytes, stream, nullptr, nullptr, nullptr, nullptr);
+}
+
+int rbm_b200_block_gibbs_stats(const rbm_b200_params* p, float* v, float* h, int64_t B, int32_t k,
+                               int init_chains, uint64_t seed, uint64_t chain_offset, uint64_t step_offset,
+                               int variant, void* workspace, size_t workspace_bytes, float scale, float* S_vh,
+                               float* S_v, float* S_h, void* stream) {
+  RBM_REQUIRE(p != nullptr && S_vh && S_v && S_h, RBM_B200_ERR_INVALID, "NULL statistics pointer");
+  RBM_REQUIRE(k >= 1, RBM_B200_ERR_INVALID, "the negative phase needs at least one Gibbs step (h is undefined for k = 0)");
+  int rc = require_device();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // zero first: the fused path ADDS raw counts inside the sampling kernel
+  if ((rc = stats_zero(S_vh, S_v, S_h, p->n_visible, p->n_hidden, st))) return rc;
+  bool fused = false;
+  if ((rc = block_gibbs_impl(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, variant, workspace,
+                             workspace_bytes, stream, S_vh, S_v, S_h, &fused))) return rc;
+  if (fused) return stats_scale(S_vh, S_v, S_h, p->n_visible, p->n_hidden, scale, st);
+  return general_negative_phase(v, h, B, p->n_visible, p->n_hidden, scale, S_vh, S_v, S_h, st);
 }
 
 int rbm_b200_block_gibbs_injected(const rbm_b200_params* p, float* v, float* h, int64_t B, int32_t k,

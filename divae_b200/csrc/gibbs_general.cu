@@ -237,9 +237,12 @@ __global__ void colsum_kernel(const float* __restrict__ x, int64_t B, int n, int
   atomicAdd(&out[c], s);
 }
 
-__global__ void scale_kernel(float* __restrict__ x, int64_t n, float scale) {
+// one launch over the three statistics arrays: set to zero (scale == 0) or multiply by scale
+__global__ void stats_scale3_kernel(float* __restrict__ S, float* __restrict__ sv, float* __restrict__ sh, int64_t nS,
+                                    int nV, int nH, float scale) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) x[i] *= scale;
+  float* p = i < nS ? S + i : (i < nS + nV ? sv + (i - nS) : (i < nS + nV + nH ? sh + (i - nS - nV) : nullptr));
+  if (p) *p = scale == 0.f ? 0.f : *p * scale;
 }
 
 // ------------------------------------------------------------------------------- host launchers
@@ -295,11 +298,24 @@ int general_energy(const rbm_b200_params* p, const float* v, const float* h, flo
   return check_launch("energy_finalize_kernel");
 }
 
+int stats_zero(float* S_vh, float* S_v, float* S_h, int nV, int nH, cudaStream_t st) {
+  const int64_t n = (int64_t)nV * nH + nV + nH;
+  stats_scale3_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(S_vh, S_v, S_h, (int64_t)nV * nH, nV, nH, 0.f);
+  return check_launch("stats_scale3_kernel(zero)");
+}
+
+int stats_scale(float* S_vh, float* S_v, float* S_h, int nV, int nH, float scale, cudaStream_t st) {
+  if (scale == 1.f) return 0;
+  if (scale == 0.f) return stats_zero(S_vh, S_v, S_h, nV, nH, st);
+  const int64_t n = (int64_t)nV * nH + nV + nH;
+  stats_scale3_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(S_vh, S_v, S_h, (int64_t)nV * nH, nV, nH, scale);
+  return check_launch("stats_scale3_kernel");
+}
+
 int general_negative_phase(const float* v, const float* h, int64_t B, int nV, int nH, float scale,
                            float* S_vh, float* S_v, float* S_h, cudaStream_t st) {
-  RBM_CUDA_TRY(cudaMemsetAsync(S_vh, 0, sizeof(float) * (size_t)nV * nH, st));
-  RBM_CUDA_TRY(cudaMemsetAsync(S_v, 0, sizeof(float) * (size_t)nV, st));
-  RBM_CUDA_TRY(cudaMemsetAsync(S_h, 0, sizeof(float) * (size_t)nH, st));
+  int rc0 = stats_zero(S_vh, S_v, S_h, nV, nH, st);
+  if (rc0) return rc0;
   if (B == 0) return 0;
   const int tiles = ceil_div(nV, GBM) * ceil_div(nH, GBN);
   int splits = (int)std::min<int64_t>(ceil_div64(B, 256), std::max(1, 592 / tiles));
@@ -317,10 +333,7 @@ int general_negative_phase(const float* v, const float* h, int64_t B, int nV, in
   rc = check_launch("colsum_kernel");
   if (rc) return rc;
   // raw sums are exact integers for binary states; scale once at the end
-  scale_kernel<<<(unsigned)ceil_div64((int64_t)nV * nH, 256), 256, 0, st>>>(S_vh, (int64_t)nV * nH, scale);
-  scale_kernel<<<(unsigned)ceil_div(nV, 256), 256, 0, st>>>(S_v, nV, scale);
-  scale_kernel<<<(unsigned)ceil_div(nH, 256), 256, 0, st>>>(S_h, nH, scale);
-  return check_launch("scale_kernel");
+  return stats_scale(S_vh, S_v, S_h, nV, nH, scale, st);
 }
 
 }  // namespace rbm

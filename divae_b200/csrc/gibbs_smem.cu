@@ -44,7 +44,14 @@ struct SmemArgs {
   int wn;                // warps per chain group (1, 2 or 4)
   int groups;            // chain groups per CTA
   int64_t n_batches;     // ceil(B / (16 * groups))
+  // fused negative-phase statistics of the FINAL (v, h) pair (raw counts, atomically added):
+  // only for priors of at most 64 x 64 units (one state word per side); else nullptr
+  float* S_vh;           // [nV, nH]
+  float* S_v;            // [nV]
+  float* S_h;            // [nH]
 };
+
+constexpr int kStatLd = 72;   // bf16 row pitch of the per-warp [16 chains x 64 units] statistics tiles (+16 B pad)
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -209,6 +216,12 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
   float* nbv = nbh + kMaxUnits;
   uint32_t* vbits = reinterpret_cast<uint32_t*>(nbv + kMaxUnits);   // [groups][kMaxWords][32]
   uint32_t* hbits = vbits + args.groups * kMaxWords * 32;
+  // fused statistics (S_vh != nullptr): CTA accumulator [64][64] + column sums, per-warp bf16 tiles
+  float* S_s = reinterpret_cast<float*>(hbits + args.groups * kMaxWords * 32);
+  float* sv_s = S_s + 64 * 64;
+  float* sh_s = sv_s + 64;
+  __nv_bfloat16* stat_tiles = reinterpret_cast<__nv_bfloat16*>(sh_s + 64);   // [groups][2][16][kStatLd]
+  const bool fuse_stats = args.S_vh != nullptr;
 
   const int tid = threadIdx.x;
   // ---- stage W (zero padded) and the pre-scaled biases once per CTA
@@ -235,6 +248,8 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
     nbh[i] = i < nH ? kNegLog2e * args.hbias[i] : 0.f;
     nbv[i] = i < nV ? kNegLog2e * args.vbias[i] : 0.f;
   }
+  if (fuse_stats)
+    for (int i = tid; i < 64 * 64 + 128; i += blockDim.x) S_s[i] = 0.f;
   __syncthreads();
 
   const int warp = tid >> 5, lane = tid & 31;
@@ -329,14 +344,88 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
             }
         }
       }
+      if (fuse_stats && args.k > 0) {
+        // ---- fused negative-phase statistics of this group's final (v, h): S += v^T h, column sums.
+        // (<= 64 units per side => one word per side and one warp per group.)
+        __nv_bfloat16* vs = stat_tiles + (size_t)grp * 2 * 16 * kStatLd;
+        __nv_bfloat16* hs = vs + 16 * kStatLd;
+        const uint32_t wv = myv[lane], wh = myh[lane];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int rowhalf = 0; rowhalf < 2; ++rowhalf) {
+            const bool valid = (rowhalf ? r_hi : r_lo) < args.B;    // padded chains contribute nothing
+            const int row = g + 8 * rowhalf, col = 8 * j + 2 * t;
+            const uint32_t b0 = state_bit(j, rowhalf, 0), b1 = state_bit(j, rowhalf, 1);
+            const uint32_t pv = valid ? ((((wv >> b0) & 1u) * 0x3F80u) | (((wv >> b1) & 1u) * 0x3F800000u)) : 0u;
+            const uint32_t ph = valid ? ((((wh >> b0) & 1u) * 0x3F80u) | (((wh >> b1) & 1u) * 0x3F800000u)) : 0u;
+            *reinterpret_cast<uint32_t*>(vs + row * kStatLd + col) = pv;
+            *reinterpret_cast<uint32_t*>(hs + row * kStatLd + col) = ph;
+          }
+        __syncwarp();
+        const uint32_t vs_a = (uint32_t)__cvta_generic_to_shared(vs), hs_a = (uint32_t)__cvta_generic_to_shared(hs);
+        const int m = lane >> 3, rr = lane & 7;
+        // A = v^T (m = visible unit, k = chain): x4.trans of [chains 0-7|8-15] x [units 0-7|8-15] blocks
+        // B = h   (k = chain, n = hidden unit): x4.trans of the same block shape
+#pragma unroll 1
+        for (int mt = 0; mt < vt; ++mt) {
+          uint32_t a[4];
+          ldmatrix_x4_trans(vs_a + (uint32_t)((((m >> 1) * 8 + rr) * kStatLd + mt * 16 + (m & 1) * 8) * 2), a[0], a[1], a[2], a[3]);
+          float acc[8][4];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            if (p < ht) {
+              uint32_t b0, b1, b2, b3;
+              ldmatrix_x4_trans(hs_a + (uint32_t)((((m & 1) * 8 + rr) * kStatLd + p * 16 + (m >> 1) * 8) * 2), b0, b1, b2, b3);
+              mma_bf16_16816(acc[2 * p], a, b0, b1);
+              mma_bf16_16816(acc[2 * p + 1], a, b2, b3);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int vi = mt * 16 + g + 8 * (i >> 1), hj = 8 * j + 2 * t + (i & 1);
+              if (acc[j][i] != 0.f) atomicAdd(&S_s[vi * 64 + hj], acc[j][i]);
+            }
+        }
+        // column sums: lane handles units lane and lane + 32
+#pragma unroll
+        for (int u = lane; u < 64; u += 32) {
+          float cv = 0.f, chh = 0.f;
+#pragma unroll
+          for (int row = 0; row < 16; ++row) {
+            cv += __bfloat162float(vs[row * kStatLd + u]);
+            chh += __bfloat162float(hs[row * kStatLd + u]);
+          }
+          if (cv != 0.f) atomicAdd(&sv_s[u], cv);
+          if (chh != 0.f) atomicAdd(&sh_s[u], chh);
+        }
+      }
       group_barrier(bar_id, bar_threads);   // bits buffers are reused by the next batch
     }
   }
+  if (fuse_stats) {
+    // raw counts of this CTA -> global accumulators (integer-valued floats: exact, order-independent)
+    __syncthreads();
+    for (int idx = tid; idx < nV * nH; idx += blockDim.x) {
+      const float x = S_s[(idx / nH) * 64 + idx % nH];
+      if (x != 0.f) atomicAdd(&args.S_vh[idx], x);
+    }
+    for (int i = tid; i < nV; i += blockDim.x) if (sv_s[i] != 0.f) atomicAdd(&args.S_v[i], sv_s[i]);
+    for (int j = tid; j < nH; j += blockDim.x) if (sh_s[j] != 0.f) atomicAdd(&args.S_h[j], sh_s[j]);
+  }
 }
 
-size_t smem_bytes_needed(int nV, int nH, int groups) {
+size_t smem_bytes_needed(int nV, int nH, int groups, bool fuse_stats) {
   const int nVp = round_up(nV, 16), nHp = round_up(nH, 16);
-  return (size_t)nVp * (nHp + 8) * 2 + 2 * kMaxUnits * sizeof(float) + (size_t)2 * groups * kMaxWords * 32 * sizeof(uint32_t);
+  size_t n = (size_t)nVp * (nHp + 8) * 2 + 2 * kMaxUnits * sizeof(float) + (size_t)2 * groups * kMaxWords * 32 * sizeof(uint32_t);
+  if (fuse_stats) n += (64 * 64 + 128) * sizeof(float) + (size_t)groups * 2 * 16 * kStatLd * 2;
+  return n;
 }
 
 }  // namespace
@@ -345,8 +434,11 @@ bool smem_variant_supported(int nV, int nH) { return nV >= 1 && nH >= 1 && nV <=
 
 size_t smem_workspace_bytes(int, int, int64_t) { return 0; }
 
+bool smem_can_fuse_stats(int nV, int nH) { return nV <= 64 && nH <= 64; }
+
 int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains, uint64_t seed,
-                     uint64_t chain_offset, uint64_t step_offset, void*, size_t, cudaStream_t st) {
+                     uint64_t chain_offset, uint64_t step_offset, void*, size_t, cudaStream_t st, float* S_vh,
+                     float* S_v, float* S_h) {
   RBM_REQUIRE(smem_variant_supported(p->n_visible, p->n_hidden), RBM_B200_ERR_UNSUPPORTED,
               "SMEM variant supports priors up to %d x %d units, got %d x %d", kMaxUnits, kMaxUnits, p->n_visible,
               p->n_hidden);
@@ -357,6 +449,8 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   a.W = p->W_bf16; a.vbias = p->vbias; a.hbias = p->hbias; a.v = v; a.h = h; a.B = B;
   a.nV = p->n_visible; a.nH = p->n_hidden; a.k = k; a.init_chains = init_chains;
   a.seed = seed; a.chain_offset = chain_offset; a.step_offset = step_offset;
+  const bool fuse = S_vh != nullptr && smem_can_fuse_stats(p->n_visible, p->n_hidden);
+  a.S_vh = fuse ? S_vh : nullptr; a.S_v = fuse ? S_v : nullptr; a.S_h = fuse ? S_h : nullptr;
   const int vwords = ceil_div(a.nV, 64), hwords = ceil_div(a.nH, 64);
   const int maxw = std::max(vwords, hwords);
   const int64_t n_groups = ceil_div64(B, 16);
@@ -368,7 +462,7 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   while (groups > 1 && ceil_div64(n_groups, groups) < sm_count) groups >>= 1;
   a.wn = wn; a.groups = groups;
   a.n_batches = ceil_div64(n_groups, groups);
-  const size_t smem = smem_bytes_needed(a.nV, a.nH, groups);
+  const size_t smem = smem_bytes_needed(a.nV, a.nH, groups, fuse);
   const int grid = (int)std::min<int64_t>(a.n_batches, sm_count);
   const int threads = 32 * wn * groups;
   auto launch = [&](auto kern) -> int {

@@ -18,13 +18,19 @@ int general_energy(const rbm_b200_params* p, const float* v, const float* h, flo
                    float* part, cudaStream_t st);
 int general_negative_phase(const float* v, const float* h, int64_t B, int nV, int nH, float scale,
                            float* S_vh, float* S_v, float* S_h, cudaStream_t st);
+int stats_zero(float* S_vh, float* S_v, float* S_h, int nV, int nH, cudaStream_t st);
+int stats_scale(float* S_vh, float* S_v, float* S_h, int nV, int nH, float scale, cudaStream_t st);
 
 // gibbs_smem.cu — persistent kernel, W (bf16) resident in shared memory
 bool smem_variant_supported(int nV, int nH);
 size_t smem_workspace_bytes(int nV, int nH, int64_t B);
+// S_vh/S_v/S_h non-null (and smem_can_fuse_stats): raw counts of the final (v,h) are atomically
+// ADDED to them inside the same kernel (caller zeroes before, scales after).
+bool smem_can_fuse_stats(int nV, int nH);
 int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains,
                      uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws,
-                     size_t ws_bytes, cudaStream_t st);
+                     size_t ws_bytes, cudaStream_t st, float* S_vh = nullptr, float* S_v = nullptr,
+                     float* S_h = nullptr);
 
 // gibbs_umma.cu — tcgen05/TMEM GEMM per half-step fed by TMA
 bool umma_variant_supported(int nV, int nH);

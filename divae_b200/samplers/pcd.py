@@ -70,7 +70,7 @@ class PCD(BaseSampler):
                                   chain_offset=self._chain_offset, half_step_idx=self._next_half_step())
 
     # --------------------------------------------------------------------- k-step chain
-    def _run_chain(self, v, init_chains, k, step_offset):
+    def _run_chain(self, v, init_chains, k, step_offset, stats_scale=None):
         lib = _lib.load()
         dev = self._RBM.visible_bias.device
         _lib.require_cuda(self._RBM.visible_bias, "RBM parameters")
@@ -86,6 +86,17 @@ class PCD(BaseSampler):
                        or self._workspace.device != dev):
             self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         ws = self._workspace if nbytes else None
+        if stats_scale is not None:
+            # chain + negative-phase statistics in one call (fused into the final sweep for small priors)
+            S = torch.empty((nV, nH), dtype=torch.float32, device=dev)
+            sv = torch.empty(nV, dtype=torch.float32, device=dev)
+            sh = torch.empty(nH, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.rbm_b200_block_gibbs_stats(
+                    ctypes.byref(p), _ops._ptr(v), _ops._ptr(h), B, k, 1 if init_chains else 0, self._seed,
+                    self._chain_offset, step_offset, self._variant, _ops._ptr(ws), nbytes, float(stats_scale),
+                    _ops._ptr(S), _ops._ptr(sv), _ops._ptr(sh), _ops._stream()), "block_gibbs_stats")
+            return v, h, (S, sv, sh)
         with torch.cuda.device(dev):
             _lib.check(lib.rbm_b200_block_gibbs(
                 ctypes.byref(p), _ops._ptr(v), _ops._ptr(h), B, k, 1 if init_chains else 0, self._seed,
@@ -93,19 +104,19 @@ class PCD(BaseSampler):
                 "block_gibbs")
         return v, h
 
-    def block_gibbs_sampling(self):
+    def block_gibbs_sampling(self, _stats_scale=None):
         """Block Gibbs sampling (pcd.py:51-69). Returns (visible_states, hidden_states)."""
         k = self.n_gibbs_sampling_steps
         step_offset = self._half_steps
         with torch.no_grad():
             if self._persistent and self._MCState is not None:
-                v, h = self._run_chain(self._MCState.clone(), False, k, step_offset)
+                out = self._run_chain(self._MCState.clone(), False, k, step_offset, _stats_scale)
             else:
-                v, h = self._run_chain(None, True, k, step_offset)
+                out = self._run_chain(None, True, k, step_offset, _stats_scale)
         self._half_steps += 2 * k
         if self._persistent:
-            self._MCState = v  # true PCD (the line the reference commented out, pcd.py:64)
-        return v, h
+            self._MCState = out[0]  # true PCD (the line the reference commented out, pcd.py:64)
+        return out
 
     def _block_gibbs_with_uniforms(self, v0, uniforms_h, uniforms_v):
         """Test hook: run k steps against injected uniforms [k,B,nH] / [k,B,nV] (fp32 W, GENERAL kernels)."""
@@ -129,11 +140,10 @@ class PCD(BaseSampler):
         backpropagates -<v h^T>, -<v>, -<h> into (W, a, c) without the [B,nV,nH] broadcast.
         With a process group the statistics are sum-allreduced over chain shards (NCCL).
         """
-        v, h = self.block_gibbs_sampling()
         world = 1
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             world = torch.distributed.get_world_size(group)
-        S, sv, sh = _ops.negative_phase_stats(v, h, scale=1.0 / (self._batch_size * world))
+        v, h, (S, sv, sh) = self.block_gibbs_sampling(_stats_scale=1.0 / (self._batch_size * world))
         if world > 1:
             from .. import dist as _dist
             S, sv, sh = _dist.allreduce_stats(S, sv, sh, group=group)

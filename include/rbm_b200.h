@@ -153,6 +153,19 @@ RBM_B200_API int rbm_b200_negative_phase(const float *v, const float *h, int64_t
                             int32_t n_hidden, float scale, float *S_vh, float *S_v, float *S_h,
                             void *stream);
 
+/* The PCD negative phase in ONE call: rbm_b200_block_gibbs followed, on the same stream, by the
+ * statistics of the returned (v, h) pair (rbm_b200_negative_phase semantics, outputs overwritten).
+ * For priors of at most 64 x 64 units (every prior the reference's model configs build except
+ * divae.yaml and the *_deep variant) the statistics are computed INSIDE the final sweep of the
+ * persistent shared-memory kernel from the on-chip states (v^T h by tensor-core MMA, raw counts
+ * added atomically, scaled once); larger priors run the statistics kernels right after the chain.
+ * Replaces gumbolt.py:102-104 / dvaepp.py:141-159 (sampler call + energy_exp on its samples). */
+RBM_B200_API int rbm_b200_block_gibbs_stats(const rbm_b200_params *p, float *v, float *h, int64_t B,
+                                            int32_t k, int init_chains, uint64_t seed, uint64_t chain_offset,
+                                            uint64_t step_offset, int variant, void *workspace,
+                                            size_t workspace_bytes, float scale, float *S_vh, float *S_v,
+                                            float *S_h, void *stream);
+
 /* Annealed importance sampling of log Z (Salakhutdinov & Murray 2008, RBM form).  The
  * reference has NO estimator: RBM.get_logZ_value returns the literal 33.65
  * (models/rbm/rbm.py:51-54); this entry supplies the missing computation.

@@ -82,3 +82,27 @@ def test_auto_uses_smem_for_small_priors_and_default_pcd_shape():
     ov, oh, clean = orc.block_gibbs_philox(W, a, c, 128, 40, 2)
     assert clean.mean() > 0.9
     assert (v[clean] == ov[clean]).all() and (h[clean] == oh[clean]).all()
+
+
+@pytest.mark.parametrize("nV,nH,B,k", [(64, 64, 128, 40), (16, 16, 100, 3), (33, 50, 37, 2), (64, 48, 148 * 128 + 5, 2),
+                                       (256, 256, 64, 2), (512, 320, 300, 2)])
+def test_negative_phase_statistics_fused_into_the_final_sweep(nV, nH, B, k):
+    """rbm_b200_block_gibbs_stats: for priors <= 64x64 the statistics come out of the sampling kernel
+    itself; either way they equal the statistics of the returned (v, h) exactly (integer counts)."""
+    from divae_b200 import _ops
+    W, a, c = rand_params(nV, nH, 0.3, nV + nH)
+    rbm = make_rbm(W, a, c)
+    s = divae_b200.PCD(batch_size=B, RBM=rbm, n_gibbs_sampling_steps=k, seed=23)
+    v, h, (S, sv, sh) = s.block_gibbs_sampling(_stats_scale=1.0)
+    vn, hn = v.cpu().numpy().astype(np.float64), h.cpu().numpy().astype(np.float64)
+    assert (S.cpu().numpy() == vn.T @ hn).all()
+    assert (sv.cpu().numpy() == vn.sum(0)).all() and (sh.cpu().numpy() == hn.sum(0)).all()
+    # and the samples themselves are the ordinary ones
+    s2 = divae_b200.PCD(batch_size=B, RBM=rbm, n_gibbs_sampling_steps=k, seed=23)
+    v2, h2 = s2.block_gibbs_sampling()
+    assert torch.equal(v, v2) and torch.equal(h, h2)
+    # negative_phase(): energy expectation + gradients through the fused statistics
+    s3 = divae_b200.PCD(batch_size=B, RBM=rbm, n_gibbs_sampling_steps=k, seed=23)
+    e, (S3, sv3, sh3) = s3.negative_phase()
+    np.testing.assert_allclose(S3.cpu().numpy(), vn.T @ hn / B, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(e.item(), orc.energy_exp(v.cpu().numpy(), h.cpu().numpy(), W, a, c), rtol=1e-4, atol=1e-4)
