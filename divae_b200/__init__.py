@@ -12,5 +12,6 @@ from .rbm import RBM  # noqa: F401
 from .samplers.baseSampler import BaseSampler  # noqa: F401
 from .samplers.gibbsSampler import GibbsSampler  # noqa: F401
 from .samplers.pcd import PCD  # noqa: F401
+from ._ops import energy_exp  # noqa: F401
 
-__all__ = ["RBM", "BaseSampler", "GibbsSampler", "PCD"]
+__all__ = ["RBM", "BaseSampler", "GibbsSampler", "PCD", "energy_exp"]

@@ -185,3 +185,14 @@ class _EnergyExpFromStats(torch.autograd.Function):
 
 def energy_exp_from_stats(rbm, S, sv, sh):
     return _EnergyExpFromStats.apply(rbm.weights, rbm.visible_bias, rbm.hidden_bias, S, sv, sh)
+
+
+def energy_exp(rbm, rbm_vis, rbm_hid):
+    """mean_b(-v^T W h - a.v - c.h): drop-in for GumBolt.energy_exp / the DiVAEPP KL energy terms on
+    POSTERIOR samples (gumbolt.py:97-99,109-134; dvaepp.py:188-200 — SURVEY.md §8f rank 1).
+
+    Same value and the same gradients w.r.t. the (real-valued, smoothed) samples and (W, a, c) as the
+    reference expression, without materialising W broadcast to [B, nV, nH]: forward is the fused energy
+    kernel (rbm_b200_energy), backward three [B,n] x [n,n] products."""
+    pack = rbm._pack.pack(rbm, need_bf16=False)
+    return energy(rbm, pack, rbm_vis, rbm_hid).mean()

@@ -132,6 +132,27 @@ class PCD(BaseSampler):
                        "block_gibbs_injected")
         return v, h
 
+    def sample(self, n_samples, n_gibbs_sampling_steps=None):
+        """Draw `n_samples` independent chains in ONE launch (fresh Bernoulli(1/2) starts).
+
+        The calorimeter models generate `num_samples` showers by calling block_gibbs_sampling()
+        `num_samples // batch_size` times in a Python loop, once per conditioning energy
+        (gumboltCaloV5.py:78-96, engineCaloV3.py:115-129); this returns the same
+        kind of (v, h) pair for all of them at once.  Chain ids continue after this sampler's own batch,
+        so the draws never overlap with block_gibbs_sampling()'s."""
+        k = self.n_gibbs_sampling_steps if n_gibbs_sampling_steps is None else int(n_gibbs_sampling_steps)
+        saved = (self._batch_size, self._chain_offset, self._workspace)
+        try:
+            self._batch_size = int(n_samples)
+            self._chain_offset = saved[1] + saved[0]
+            self._workspace = None
+            with torch.no_grad():
+                v, h = self._run_chain(None, True, k, self._half_steps)
+        finally:
+            self._batch_size, self._chain_offset, self._workspace = saved
+        self._half_steps += 2 * k
+        return v, h
+
     # ------------------------------------------------------------- negative phase (a15)
     def negative_phase(self, group=None):
         """Run the chain and return (energy_exp, (S_vh, S_v, S_h)).

@@ -152,3 +152,39 @@ def test_pcd_training_moves_model_marginals_toward_data():
     probe = divae_b200.PCD(batch_size=8192, RBM=rbm, n_gibbs_sampling_steps=50, seed=2)
     v, _ = probe.block_gibbs_sampling()
     assert (v.mean(0) - target).abs().max().item() < 0.08
+
+
+def test_energy_exp_on_posterior_samples_matches_reference_expression():
+    """the positive-phase energy term on smoothed (real-valued) posterior samples,
+    value and gradients w.r.t. samples and parameters vs the reference's broadcast expression."""
+    W, a, c = rand_params(64, 64, 0.3, 21)
+    rbm = make_rbm(W, a, c)
+    torch.manual_seed(1)
+    z_vis = torch.rand(100, 64, device=DEV, requires_grad=True)
+    z_hid = torch.rand(100, 64, device=DEV, requires_grad=True)
+    e = divae_b200.energy_exp(rbm, z_vis, z_hid)
+    g = torch.autograd.grad(e, [z_vis, z_hid, rbm._weights, rbm._visible_bias, rbm._hidden_bias])
+    # gumbolt.py:118-134 verbatim
+    w = rbm.weights + torch.zeros((z_vis.size(0),) + rbm.weights.size(), device=DEV)
+    vis = z_vis.unsqueeze(2).permute(0, 2, 1); hid = z_hid.unsqueeze(2)
+    ref = torch.mean(-torch.matmul(vis, torch.matmul(w, hid)).reshape(-1) - torch.matmul(z_vis, rbm.visible_bias)
+                     - torch.matmul(z_hid, rbm.hidden_bias), 0)
+    gr = torch.autograd.grad(ref, [z_vis, z_hid, rbm._weights, rbm._visible_bias, rbm._hidden_bias])
+    torch.testing.assert_close(e, ref, rtol=1e-4, atol=1e-4)
+    for mine, r in zip(g, gr):
+        torch.testing.assert_close(mine, r, rtol=1e-3, atol=1e-5)
+
+
+def test_sample_many_chains_in_one_launch():
+    """generation of num_samples chains at once instead of a loop of batch-size calls."""
+    W, a, c = rand_params(64, 64, 0.3, 22)
+    rbm = make_rbm(W, a, c)
+    s = divae_b200.PCD(batch_size=128, RBM=rbm, n_gibbs_sampling_steps=10, seed=31)
+    v, h = s.sample(1024)
+    assert v.shape == (1024, 64) and h.shape == (1024, 64)
+    ov, oh, clean = orc.block_gibbs_philox(W, a, c, 1024, 10, 31, chain_offset=128)
+    assert (v.cpu().numpy()[clean] == ov[clean]).all() and (h.cpu().numpy()[clean] == oh[clean]).all()
+    v2, h2 = s.block_gibbs_sampling()                       # the sampler's own batch is untouched
+    assert v2.shape == (128, 64) and s.get_batch_size() == 128
+    ov2, oh2, clean2 = orc.block_gibbs_philox(W, a, c, 128, 10, 31, step_offset=20)
+    assert (v2.cpu().numpy()[clean2] == ov2[clean2]).all()
