@@ -753,36 +753,56 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   int rc = check_launch("umma staging kernels");
   if (rc) return rc;
 
+  // Chains are independent, so the k-step loop MAY run chunk by chunk (RBM_B200_CHUNK_ROWS), e.g. with chunks
+  // whose two state tiles fit in L2 so that half-steps stop round-tripping through HBM.  Measured on B200
+  // (profiles/r01_pairs_vs_single.txt): at config 4 it is a LOSS (158 vs 141 us per launch-equivalent for
+  // 18,944-chain chunks) - the per-launch overheads of 3.5x more, 3.5x smaller launches outweigh the HBM
+  // energy saved - so the default is one chunk.
+  int64_t chunk_rows = pl.rows_pad;
+  {
+    static const long env_chunk = [] { const char* e = getenv("RBM_B200_CHUNK_ROWS"); return e ? atol(e) : 0L; }();
+    if (env_chunk > 0) chunk_rows = std::min<int64_t>(pl.rows_pad, ceil_div64(env_chunk, 2 * BLOCK_M) * 2 * BLOCK_M);
+  }
+  static const int pairs_min_tiles = [] { const char* e = getenv("RBM_B200_PAIRS_MIN_TILES"); return e ? atoi(e) : 8; }();
+
   // tensor maps: states are K-major A operands; W is read MN-major (v->h) and K-major (h->v)
-  CUtensorMap tm_v, tm_h, tm_w_mn, tm_w_k;
-  if ((rc = make_tmap(&tm_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
-  if ((rc = make_tmap(&tm_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
+  CUtensorMap tm_w_mn, tm_w_k_single, tm_w_k_pair;
   if ((rc = make_tmap(&tm_w_mn, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
-  // pairs pay off once every cluster loops over >= 8 tiles (profiles/r01_pairs_vs_single.txt)
-  const bool pairs = pairs_enabled() && (pl.rows_pad / (2 * BLOCK_M)) * ceil_div(std::max(pl.nVp, pl.nHp), 256) >= 8 * (sm_count / 2);
   // h->v reads W K-major in [n rows x 64] boxes: a CTA of a pair stages half of the 256 rows
-  if ((rc = make_tmap(&tm_w_k, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp,
-                      (uint32_t)((pairs && pl.bn_v == 256) ? 128 : pl.bn_v)))) return rc;
-  // epilogue stores: [32 chains x 32 units] boxes, 64-byte swizzle
-  CUtensorMap to_v, to_h;
-  if ((rc = make_tmap(&to_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_tmap(&to_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_tmap(&tm_w_k_single, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, (uint32_t)pl.bn_v))) return rc;
+  if ((rc = make_tmap(&tm_w_k_pair, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 128))) return rc;
 
-  HalfStepArgs ah{}, av{};
-  ah.out = Hs; ah.nbias = nbh; ah.ldo = pl.nHp; ah.m_tiles = (int)(pl.rows_pad / BLOCK_M);
-  ah.n_tiles = ceil_div(pl.nHp, pl.bn_h); ah.k_blocks = pl.nVp / BLOCK_K; ah.chain_offset = chain_offset; ah.n_valid = pl.nH;
-  av.out = Vs; av.nbias = nbv; av.ldo = pl.nVp; av.m_tiles = ah.m_tiles;
-  av.n_tiles = ceil_div(pl.nVp, pl.bn_v); av.k_blocks = pl.nHp / BLOCK_K; av.chain_offset = chain_offset; av.n_valid = pl.nV;
+  for (int64_t r0 = 0; r0 < pl.rows_pad; r0 += chunk_rows) {
+    const int64_t rows = std::min(chunk_rows, pl.rows_pad - r0);
+    __nv_bfloat16* Vc = Vs + r0 * pl.nVp;
+    __nv_bfloat16* Hc = Hs + r0 * pl.nHp;
+    // pairs pay off once every cluster loops over enough tiles (profiles/r01_pairs_vs_single.txt)
+    const bool pairs = pairs_enabled() &&
+                       (rows / (2 * BLOCK_M)) * ceil_div(std::max(pl.nVp, pl.nHp), 256) >= (int64_t)pairs_min_tiles * (sm_count / 2);
+    CUtensorMap tm_v, tm_h, to_v, to_h;
+    if ((rc = make_tmap(&tm_v, Vc, (uint64_t)rows, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
+    if ((rc = make_tmap(&tm_h, Hc, (uint64_t)rows, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
+    // epilogue stores: [32 chains x 32 units] boxes, 64-byte swizzle
+    if ((rc = make_tmap(&to_v, Vc, (uint64_t)rows, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_tmap(&to_h, Hc, (uint64_t)rows, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    const CUtensorMap& tm_w_k = (pairs && pl.bn_v == 256) ? tm_w_k_pair : tm_w_k_single;
 
-  for (int s = 0; s < k; ++s) {
-    ah.ctx = make_draw_ctx(seed, step_offset + 2ull * s, TAG_GIBBS);
-    rc = pl.bn_h == 256 ? launch_half_step<256, true>(tm_v, tm_w_mn, to_h, ah, sm_count, pairs, st)
-                        : launch_half_step<128, true>(tm_v, tm_w_mn, to_h, ah, sm_count, pairs, st);
-    if (rc) return rc;
-    av.ctx = make_draw_ctx(seed, step_offset + 2ull * s + 1, TAG_GIBBS);
-    rc = pl.bn_v == 256 ? launch_half_step<256, false>(tm_h, tm_w_k, to_v, av, sm_count, pairs, st)
-                        : launch_half_step<128, false>(tm_h, tm_w_k, to_v, av, sm_count, pairs, st);
-    if (rc) return rc;
+    HalfStepArgs ah{}, av{};
+    ah.out = Hc; ah.nbias = nbh; ah.ldo = pl.nHp; ah.m_tiles = (int)(rows / BLOCK_M);
+    ah.n_tiles = ceil_div(pl.nHp, pl.bn_h); ah.k_blocks = pl.nVp / BLOCK_K; ah.chain_offset = chain_offset + (uint64_t)r0; ah.n_valid = pl.nH;
+    av.out = Vc; av.nbias = nbv; av.ldo = pl.nVp; av.m_tiles = ah.m_tiles;
+    av.n_tiles = ceil_div(pl.nVp, pl.bn_v); av.k_blocks = pl.nHp / BLOCK_K; av.chain_offset = chain_offset + (uint64_t)r0; av.n_valid = pl.nV;
+
+    for (int s = 0; s < k; ++s) {
+      ah.ctx = make_draw_ctx(seed, step_offset + 2ull * s, TAG_GIBBS);
+      rc = pl.bn_h == 256 ? launch_half_step<256, true>(tm_v, tm_w_mn, to_h, ah, sm_count, pairs, st)
+                          : launch_half_step<128, true>(tm_v, tm_w_mn, to_h, ah, sm_count, pairs, st);
+      if (rc) return rc;
+      av.ctx = make_draw_ctx(seed, step_offset + 2ull * s + 1, TAG_GIBBS);
+      rc = pl.bn_v == 256 ? launch_half_step<256, false>(tm_h, tm_w_k, to_v, av, sm_count, pairs, st)
+                          : launch_half_step<128, false>(tm_h, tm_w_k, to_v, av, sm_count, pairs, st);
+      if (rc) return rc;
+    }
   }
   // back to the reference's dtype
   {
