@@ -98,7 +98,9 @@ __device__ __forceinline__ int state_bit(int j, int rowhalf, int e) { return 4 *
 // One half-step for this warp: out words [ow_begin, ow_end) of  f(state_in x Wop + bias).
 //   TRANS_B = false: v -> h, Wop[k][n] = W[k][n]   (ldmatrix.trans on rows k)
 //   TRANS_B = true : h -> v, Wop[k][n] = W[n][k]   (ldmatrix on rows n)
-template <int MAXW, bool TRANS_B>
+// FULL: both sides are whole 64-unit words (k_tiles == 4*MAXW, every word has 4 live column pairs):
+// all tile guards fold away, leaving a branch-free ldmatrix/mma loop.
+template <int MAXW, bool TRANS_B, bool FULL>
 __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words, uint32_t* __restrict__ out_words,
                                           int k_tiles, int n_units, int ow_begin, int ow_end, uint32_t w_smem,
                                           int ldw_bytes, const float* __restrict__ nbias, const DrawCtx ctx,
@@ -108,7 +110,7 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
   uint32_t a[MAXW * 4][4];
 #pragma unroll
   for (int w = 0; w < MAXW; ++w) {
-    const uint32_t word = (w * 4 < k_tiles) ? in_words[w * 32 + lane] : 0u;
+    const uint32_t word = (FULL || w * 4 < k_tiles) ? in_words[w * 32 + lane] : 0u;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -123,7 +125,7 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
 
   for (int ow = ow_begin; ow < ow_end; ++ow) {
     const int n_base = ow * 64;
-    const int n_tiles16 = min(4, (n_units - n_base + 15) >> 4);  // live 16-unit column pairs in this word
+    const int n_tiles16 = FULL ? 4 : min(4, (n_units - n_base + 15) >> 4);  // live 16-unit column pairs in this word
     float acc[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -131,10 +133,10 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
       for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 #pragma unroll
     for (int kt = 0; kt < MAXW * 4; ++kt) {
-      if (kt < k_tiles) {
+      if (FULL || kt < k_tiles) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {       // 16-unit column pair p -> n-tiles 2p, 2p+1
-          if (p < n_tiles16) {
+          if (FULL || p < n_tiles16) {
             uint32_t b0, b1, b2, b3;
             const int row = TRANS_B ? (n_base + p * 16 + lrow) : (kt * 16 + lrow);
             const int col = TRANS_B ? (kt * 16 + lcol) : (n_base + p * 16 + lcol);
@@ -151,7 +153,7 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
     uint32_t word = 0;
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      if (hf * 2 < n_tiles16) {
+      if (FULL || hf * 2 < n_tiles16) {
         const uint32_t blk = (uint32_t)((ow * 2 + hf) * 4 + t);
         const uint4 x0 = draw_block(ctx, blk, chain_lo);
         const uint4 x1 = draw_block(ctx, blk, chain_hi);
@@ -193,7 +195,7 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
       }
     }
     // units beyond n_units inside the last live 16-pair must stay 0 (they are K padding next half-step)
-    if (n_base + 64 > n_units) {
+    if (!FULL && n_base + 64 > n_units) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -204,7 +206,7 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
   }
 }
 
-template <int MAXW>
+template <int MAXW, bool FULL>
 __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int nV = args.nV, nH = args.nH;
@@ -227,11 +229,13 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
   // ---- stage W (zero padded) and the pre-scaled biases once per CTA
   if ((nH & 7) == 0 && (reinterpret_cast<uintptr_t>(args.W) & 15) == 0) {
     const int chunks = nH >> 3;                       // 16-byte chunks per row
+    // asynchronous 16-byte copies global -> shared (LDGSTS): all of a thread's copies are in flight at once
     for (int idx = tid; idx < nV * chunks; idx += blockDim.x) {
       const int i = idx / chunks, c8 = idx % chunks;
-      *reinterpret_cast<uint4*>(Ws + (size_t)i * ldw + 8 * c8) =
-          __ldg(reinterpret_cast<const uint4*>(args.W + (size_t)i * nH) + c8);
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Ws + (size_t)i * ldw + 8 * c8);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(args.W + (size_t)i * nH + 8 * c8) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     const int padc = ldw - nH;                        // zero the column pad and the row pad
     for (int idx = tid; idx < nV * padc; idx += blockDim.x)
       reinterpret_cast<uint16_t*>(Ws)[(idx / padc) * ldw + nH + idx % padc] = 0;
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
   }
   if (fuse_stats)
     for (int i = tid; i < 64 * 64 + 128; i += blockDim.x) S_s[i] = 0.f;
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   const int warp = tid >> 5, lane = tid & 31;
@@ -314,10 +319,10 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
       // ---- 2k half-steps, all on chip
       for (int s = 0; s < args.k; ++s) {
         const DrawCtx ch = make_draw_ctx(args.seed, args.step_offset + 2ull * s, TAG_GIBBS);
-        half_step<MAXW, false>(myv, myh, vt, nH, h_begin, h_end, w_smem, ldw_bytes, nbh, ch, chain_lo, chain_hi, lane);
+        half_step<MAXW, false, FULL>(myv, myh, vt, nH, h_begin, h_end, w_smem, ldw_bytes, nbh, ch, chain_lo, chain_hi, lane);
         group_barrier(bar_id, bar_threads);
         const DrawCtx cv = make_draw_ctx(args.seed, args.step_offset + 2ull * s + 1, TAG_GIBBS);
-        half_step<MAXW, true>(myh, myv, ht, nV, v_begin, v_end, w_smem, ldw_bytes, nbv, cv, chain_lo, chain_hi, lane);
+        half_step<MAXW, true, FULL>(myh, myv, ht, nV, v_begin, v_end, w_smem, ldw_bytes, nbv, cv, chain_lo, chain_hi, lane);
         group_barrier(bar_id, bar_threads);
       }
       // ---- final states back to the reference's dtype (fp32 {0,1})
@@ -470,9 +475,17 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
     kern<<<grid, threads, smem, st>>>(a);
     return check_launch("smem_gibbs_kernel");
   };
-  if (maxw <= 1) return launch(smem_gibbs_kernel<1>);
-  if (maxw <= 2) return launch(smem_gibbs_kernel<2>);
-  return launch(smem_gibbs_kernel<4>);
+  // whole-word square-ish priors (64, 128, 192, 256 units on both sides with equal word counts) take the
+  // guard-free instantiation
+  const bool full = (a.nV % 64 == 0) && (a.nH % 64 == 0) && vwords == hwords && (vwords == 1 || vwords == 2 || vwords == 4);
+  if (full) {
+    if (maxw == 1) return launch(smem_gibbs_kernel<1, true>);
+    if (maxw == 2) return launch(smem_gibbs_kernel<2, true>);
+    return launch(smem_gibbs_kernel<4, true>);
+  }
+  if (maxw <= 1) return launch(smem_gibbs_kernel<1, false>);
+  if (maxw <= 2) return launch(smem_gibbs_kernel<2, false>);
+  return launch(smem_gibbs_kernel<4, false>);
 }
 
 }  // namespace rbm
