@@ -59,6 +59,8 @@ _lock = threading.Lock()
 def load(build_if_missing=True):
     """Load (building first if the .so is absent and nvcc is present). Raises on failure."""
     global _lib
+    if _lib is not None:      # fast path, no lock
+        return _lib
     with _lock:
         if _lib is not None:
             return _lib
@@ -79,7 +81,7 @@ def load(build_if_missing=True):
 
 
 def check(rc, what=""):
-    if rc != 0:
+    if rc:
         msg = load().rbm_b200_last_error().decode("utf-8", "replace")
         raise RuntimeError("rbm_b200 %s failed (code %d): %s" % (what, rc, msg))
 

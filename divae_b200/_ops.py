@@ -26,29 +26,53 @@ def _f32c(t, name):
 
 
 class ParamPack:
-    """Device views of (W, a, c) plus a cached bf16 copy of W, refreshed when W changes."""
+    """Device views of (W, a, c) plus a cached bf16 copy of W, refreshed when W changes.
+
+    The packed struct is cached and re-used while the parameter tensors are the same objects at the
+    same version (an optimiser step bumps `_version`), so the per-call host cost is three integer
+    compares."""
 
     def __init__(self):
         self._bf16 = None
         self._key = None
+        self._packed = None
+        self._packed_key = None
 
     def pack(self, rbm, need_bf16):
-        W = rbm.weights.detach()
-        a = rbm.visible_bias.detach()
-        c = rbm.hidden_bias.detach()
-        W = _f32c(W, "RBM weights")
-        a = _f32c(a, "RBM visible bias")
-        c = _f32c(c, "RBM hidden bias")
+        Wp, ap, cp = rbm.weights, rbm.visible_bias, rbm.hidden_bias
+        pkey = (id(Wp), Wp._version, id(ap), ap._version, id(cp), cp._version, Wp.data_ptr(), need_bf16)
+        if pkey == self._packed_key:
+            return self._packed
+        W = _f32c(Wp.detach(), "RBM weights")
+        a = _f32c(ap.detach(), "RBM visible bias")
+        c = _f32c(cp.detach(), "RBM hidden bias")
         wb = None
         if need_bf16:
-            key = (W.data_ptr(), rbm.weights._version, W.device)
+            key = (W.data_ptr(), Wp._version, W.device)
             if self._key != key or self._bf16 is None:
                 self._bf16 = W.to(torch.bfloat16)  # round-to-nearest-even
                 self._key = key
             wb = self._bf16
         p = _lib.RbmParams(W.shape[0], W.shape[1], W.data_ptr(), wb.data_ptr() if wb is not None else 0,
                            a.data_ptr(), c.data_ptr())
-        return p, (W, a, c, wb)  # keep tensors alive for the duration of the call
+        self._packed = (p, (W, a, c, wb))  # keep tensors alive for the duration of the call
+        self._packed_key = pkey
+        return self._packed
+
+
+class _on_device:
+    """torch.cuda.device(dev) only when dev is not already current (the context manager costs microseconds)."""
+
+    def __init__(self, dev):
+        self._ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
 
 
 def half_step(rbm_pack, direction, x, mode, uniforms=None, seed=0, chain_offset=0, half_step_idx=0):

@@ -1,5 +1,6 @@
 // extern "C" entry points of librbm_b200.so (include/rbm_b200.h) and variant dispatch.
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -19,6 +20,40 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return (int)e;
+}
+
+int get_device_info(DeviceInfo* out) {
+  static DeviceInfo cache[64];
+  static bool valid[64] = {};
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev >= 0 && dev < 64 && valid[dev]) { *out = cache[dev]; return 0; }
+  DeviceInfo d{};
+  d.device = dev;
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  RBM_CUDA_TRY(cudaDeviceGetAttribute(&d.l2_bytes, cudaDevAttrL2CacheSize, dev));
+  if (dev >= 0 && dev < 64) { cache[dev] = d; valid[dev] = true; }
+  *out = d;
+  return 0;
+}
+
+int ensure_dynamic_smem_impl(const void* kern, int device, int bytes) {
+  struct Entry { const void* kern; int device; int bytes; };
+  static Entry table[256];
+  static int n = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  Entry* hit = nullptr;
+  for (int i = 0; i < n; ++i)
+    if (table[i].kern == kern && table[i].device == device) { hit = &table[i]; break; }
+  if (hit && hit->bytes >= bytes) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  if (hit) hit->bytes = bytes;
+  else if (n < 256) table[n++] = Entry{kern, device, bytes};
+  return 0;
 }
 
 static int check_params(const rbm_b200_params* p, bool need_f32) {

@@ -447,9 +447,10 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   RBM_REQUIRE(smem_variant_supported(p->n_visible, p->n_hidden), RBM_B200_ERR_UNSUPPORTED,
               "SMEM variant supports priors up to %d x %d units, got %d x %d", kMaxUnits, kMaxUnits, p->n_visible,
               p->n_hidden);
-  int dev = 0, sm_count = 0;
-  RBM_CUDA_TRY(cudaGetDevice(&dev));
-  RBM_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  DeviceInfo di;
+  int rc_di = get_device_info(&di);
+  if (rc_di) return rc_di;
+  const int sm_count = di.sm_count;
   SmemArgs a{};
   a.W = p->W_bf16; a.vbias = p->vbias; a.hbias = p->hbias; a.v = v; a.h = h; a.B = B;
   a.nV = p->n_visible; a.nH = p->n_hidden; a.k = k; a.init_chains = init_chains;
@@ -471,7 +472,8 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   const int grid = (int)std::min<int64_t>(a.n_batches, sm_count);
   const int threads = 32 * wn * groups;
   auto launch = [&](auto kern) -> int {
-    RBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int rc = ensure_dynamic_smem(kern, di.device, (int)smem);
+    if (rc) return rc;
     kern<<<grid, threads, smem, st>>>(a);
     return check_launch("smem_gibbs_kernel");
   };

@@ -673,10 +673,11 @@ int launch_half_step_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
                           int sm_count, cudaStream_t st) {
   auto kern = umma_half_step_kernel<BLOCK_N, B_MN_MAJOR, EPI, CTAS>;
   using L = SmemLayout<BLOCK_N, CTAS>;
-  static bool configured = false;
-  if (!configured) {
-    RBM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
+  {
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc) return rc;
+    if ((rc = ensure_dynamic_smem(kern, di.device, L::kTotal))) return rc;   // per device, not per process
   }
   static const int debug_mode = [] { const char* e = getenv("RBM_B200_DEBUG_MODE"); return e ? atoi(e) : 0; }();
   HalfStepArgs a2 = a;
@@ -720,10 +721,12 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   const Plan pl = make_plan(p->n_visible, p->n_hidden, B);
   RBM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, RBM_B200_ERR_WORKSPACE,
               "UMMA variant needs %zu bytes of workspace, got %zu", pl.total, ws_bytes);
-  int dev = 0, sm_count = 0, cc_major = 0;
-  RBM_CUDA_TRY(cudaGetDevice(&dev));
-  RBM_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  RBM_CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  DeviceInfo di;
+  {
+    int rc_di = get_device_info(&di);
+    if (rc_di) return rc_di;
+  }
+  const int sm_count = di.sm_count, cc_major = di.cc_major;
   RBM_REQUIRE(cc_major == 10, RBM_B200_ERR_NO_DEVICE, "UMMA variant needs an sm_100 device (got cc %d.x)", cc_major);
 
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
@@ -825,10 +828,12 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
   const Plan pl = make_plan(p->n_visible, p->n_hidden, M);
   RBM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, RBM_B200_ERR_WORKSPACE,
               "AIS needs %zu bytes of workspace, got %zu", pl.total, ws_bytes);
-  int dev = 0, sm_count = 0, cc_major = 0;
-  RBM_CUDA_TRY(cudaGetDevice(&dev));
-  RBM_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  RBM_CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  DeviceInfo di;
+  {
+    int rc_di = get_device_info(&di);
+    if (rc_di) return rc_di;
+  }
+  const int sm_count = di.sm_count, cc_major = di.cc_major;
   RBM_REQUIRE(cc_major == 10, RBM_B200_ERR_NO_DEVICE, "AIS needs an sm_100 device (got cc %d.x)", cc_major);
 
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);

@@ -64,6 +64,7 @@ class ContrastiveDivergence(object):
     def _packed(self):
         # tensors are updated in place, so bump the cache key by hand
         self._pack._key = None
+        self._pack._packed_key = None
         return self._pack.pack(self._view, need_bf16=False)
 
     def sample_from_hidden(self, probabilities_visible):

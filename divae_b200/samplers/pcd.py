@@ -45,6 +45,7 @@ class PCD(BaseSampler):
         self._half_steps = 0  # draw counter: advances by 2k per call
         self._pack = _ops.ParamPack()
         self._workspace = None
+        self._ws_query = {}   # (nV, nH, B, variant) -> workspace bytes
 
     def get_batch_size(self):
         return self._batch_size
@@ -81,7 +82,10 @@ class PCD(BaseSampler):
         if v is None:
             v = torch.empty((B, nV), dtype=torch.float32, device=dev)
         h = torch.empty((B, nH), dtype=torch.float32, device=dev)
-        nbytes = lib.rbm_b200_block_gibbs_workspace(nV, nH, B, self._variant)
+        qkey = (nV, nH, B, self._variant)
+        nbytes = self._ws_query.get(qkey)
+        if nbytes is None:
+            nbytes = self._ws_query[qkey] = lib.rbm_b200_block_gibbs_workspace(nV, nH, B, self._variant)
         if nbytes and (self._workspace is None or self._workspace.numel() < nbytes
                        or self._workspace.device != dev):
             self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -91,13 +95,13 @@ class PCD(BaseSampler):
             S = torch.empty((nV, nH), dtype=torch.float32, device=dev)
             sv = torch.empty(nV, dtype=torch.float32, device=dev)
             sh = torch.empty(nH, dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev):
+            with _ops._on_device(dev):
                 _lib.check(lib.rbm_b200_block_gibbs_stats(
                     ctypes.byref(p), _ops._ptr(v), _ops._ptr(h), B, k, 1 if init_chains else 0, self._seed,
                     self._chain_offset, step_offset, self._variant, _ops._ptr(ws), nbytes, float(stats_scale),
                     _ops._ptr(S), _ops._ptr(sv), _ops._ptr(sh), _ops._stream()), "block_gibbs_stats")
             return v, h, (S, sv, sh)
-        with torch.cuda.device(dev):
+        with _ops._on_device(dev):
             _lib.check(lib.rbm_b200_block_gibbs(
                 ctypes.byref(p), _ops._ptr(v), _ops._ptr(h), B, k, 1 if init_chains else 0, self._seed,
                 self._chain_offset, step_offset, self._variant, _ops._ptr(ws), nbytes, _ops._stream()),
