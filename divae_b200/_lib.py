@@ -48,6 +48,9 @@ PROTOTYPES = {
     "rbm_b200_energy_workspace": (_sz, [_i32, _i32, _i64]),
     "rbm_b200_energy": (_int, [_P, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "rbm_b200_negative_phase": (_int, [_vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
+    "rbm_b200_cd_workspace": (_sz, [_i32, _i32, _i64]),
+    "rbm_b200_cd_step": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i32, _f32, _f32, _f32, _vp, _u64, _u64,
+                                 _vp, _vp, _sz, _vp]),
     "rbm_b200_ais_workspace": (_sz, [_i32, _i32, _i64]),
     "rbm_b200_ais_run": (_int, [_P, _i64, ctypes.POINTER(ctypes.c_double), _i32, _u64, _u64, _vp, _vp, _sz, _vp]),
 }

@@ -276,6 +276,26 @@ int rbm_b200_negative_phase(const float* v, const float* h, int64_t B, int32_t n
   return general_negative_phase(v, h, B, n_visible, n_hidden, scale, S_vh, S_v, S_h, (cudaStream_t)stream);
 }
 
+size_t rbm_b200_cd_workspace(int32_t n_visible, int32_t n_hidden, int64_t B) {
+  if (B <= 0 || n_visible <= 0 || n_hidden <= 0) return 0;
+  return general_cd_workspace(n_visible, n_hidden, B);
+}
+
+int rbm_b200_cd_step(float* W, float* vbias, float* hbias, float* dW, float* dvb, float* dhb, int32_t n_visible,
+                     int32_t n_hidden, const float* v0, int64_t B, int32_t k, float learning_rate, float momentum,
+                     float weight_cost, const float* uniforms, uint64_t seed, uint64_t draw_offset, float* loss,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  RBM_REQUIRE(W && vbias && hbias && dW && dvb && dhb && loss, RBM_B200_ERR_INVALID, "NULL parameter pointer");
+  RBM_REQUIRE(n_visible > 0 && n_hidden > 0 && B > 0 && v0, RBM_B200_ERR_INVALID, "bad shape or NULL data");
+  RBM_REQUIRE(k >= 1, RBM_B200_ERR_INVALID, "CD-k needs k >= 1");
+  RBM_REQUIRE(workspace && workspace_bytes >= general_cd_workspace(n_visible, n_hidden, B), RBM_B200_ERR_WORKSPACE,
+              "CD workspace too small");
+  int rc = require_device();
+  if (rc) return rc;
+  return general_cd_step(W, vbias, hbias, dW, dvb, dhb, n_visible, n_hidden, v0, B, k, learning_rate, momentum,
+                         weight_cost, uniforms, seed, draw_offset, loss, (float*)workspace, (cudaStream_t)stream);
+}
+
 size_t rbm_b200_ais_workspace(int32_t n_visible, int32_t n_hidden, int64_t n_chains) {
   if (n_chains <= 0 || n_visible <= 0 || n_hidden <= 0) return 0;
   return umma_ais_workspace_bytes(n_visible, n_hidden, n_chains);

@@ -33,29 +33,39 @@ __device__ __forceinline__ void sgemm_tile(const float* __restrict__ in, const f
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  // global -> registers for one K block (the NEXT block is fetched while the current one is multiplied,
+  // so the global-load latency is off the critical path of this K-serial loop)
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int idx = tid + l * 256;
+      const int r = idx >> 4, kk = idx & 15;
+      const int64_t row = row0 + r;
+      const int k = k0 + kk;
+      ra[l] = (row < B && k < K) ? in[row * (int64_t)K + k] : 0.f;
+      if (!TRANS) {
+        const int kb = idx >> 6, n = idx & 63;
+        const int kx = k0 + kb, col = n0 + n;
+        rb[l] = (kx < K && col < N) ? W[(int64_t)kx * ldw + col] : 0.f;
+      } else {
+        const int n = idx >> 4, kb = idx & 15;
+        const int kx = k0 + kb, col = n0 + n;
+        rb[l] = (kx < K && col < N) ? W[(int64_t)col * ldw + kx] : 0.f;
+      }
+    }
+  };
+  fetch(0);
   for (int k0 = 0; k0 < K; k0 += GBK) {
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-      int idx = tid + l * 256;
-      int r = idx >> 4, kk = idx & 15;
-      int64_t row = row0 + r;
-      int k = k0 + kk;
-      As[kk][r] = (row < B && k < K) ? in[row * (int64_t)K + k] : 0.f;
-    }
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      int idx = tid + l * 256;
-      if (!TRANS) {
-        int kk = idx >> 6, n = idx & 63;
-        int k = k0 + kk, col = n0 + n;
-        Bs[kk][n] = (k < K && col < N) ? W[(int64_t)k * ldw + col] : 0.f;
-      } else {
-        int n = idx >> 4, kk = idx & 15;
-        int k = k0 + kk, col = n0 + n;
-        Bs[kk][n] = (k < K && col < N) ? W[(int64_t)col * ldw + k] : 0.f;
-      }
+      const int idx = tid + l * 256;
+      As[idx & 15][idx >> 4] = ra[l];
+      if (!TRANS) Bs[idx >> 6][idx & 63] = rb[l];
+      else Bs[idx & 15][idx >> 4] = rb[l];
     }
     __syncthreads();
+    if (k0 + GBK < K) fetch(k0 + GBK);
 #pragma unroll
     for (int kk = 0; kk < GBK; ++kk) {
       float a[4], b[4];
@@ -77,7 +87,7 @@ __global__ void __launch_bounds__(256)
 half_step_kernel(const float* __restrict__ in, const float* __restrict__ W,
                  const float* __restrict__ bias, float* __restrict__ out,
                  const float* __restrict__ U, int64_t B, int K, int N, int ldw,
-                 DrawCtx ctx, uint64_t chain_offset) {
+                 DrawCtx ctx, uint64_t chain_offset, int64_t u_row_stride, float* __restrict__ probs_out) {
   const int64_t row0 = (int64_t)blockIdx.x * GBM;
   const int n0 = blockIdx.y * GBN;
   float acc[4][4];
@@ -103,7 +113,7 @@ half_step_kernel(const float* __restrict__ in, const float* __restrict__ W,
         if (MODE == RBM_B200_MODE_PROBS) {
           r = sigmoid_precise(x);
         } else if (MODE == RBM_B200_MODE_INJECTED) {
-          r = (sigmoid_precise(x) >= U[row * (int64_t)N + c]) ? 1.f : 0.f;
+          r = (sigmoid_precise(x) >= U[row * u_row_stride + c]) ? 1.f : 0.f;
         } else {
           const uint32_t slot = unit_slot_of(c);
           const uint32_t blk = unit_block_of(c);
@@ -112,6 +122,7 @@ half_step_kernel(const float* __restrict__ in, const float* __restrict__ W,
               }) ? 1.f : 0.f;
         }
         out[row * (int64_t)N + c] = r;
+        if (MODE != RBM_B200_MODE_PROBS && probs_out) probs_out[row * (int64_t)N + c] = sigmoid_precise(x);
       }
     }
   }
@@ -249,26 +260,26 @@ __global__ void stats_scale3_kernel(float* __restrict__ S, float* __restrict__ s
 template <int MODE>
 static int launch_half_step(const rbm_b200_params* p, int direction, const float* in, float* out,
                             int64_t B, const float* U, DrawCtx ctx, uint64_t chain_offset,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool broadcast_u = false, float* probs_out = nullptr) {
   const int K = direction == 0 ? p->n_visible : p->n_hidden;
   const int N = direction == 0 ? p->n_hidden : p->n_visible;
   const float* bias = direction == 0 ? p->hbias : p->vbias;
   dim3 grid((unsigned)ceil_div64(B, GBM), (unsigned)ceil_div(N, GBN));
   if (direction == 0)
-    half_step_kernel<false, MODE><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset);
+    half_step_kernel<false, MODE><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset, broadcast_u ? 0 : (int64_t)N, probs_out);
   else
-    half_step_kernel<true, MODE><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset);
+    half_step_kernel<true, MODE><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset, broadcast_u ? 0 : (int64_t)N, probs_out);
   return check_launch("half_step_kernel");
 }
 
 int general_half_step(const rbm_b200_params* p, int direction, const float* in, float* out, int64_t B,
                       int mode, const float* U, uint64_t seed, uint64_t chain_offset,
-                      uint64_t half_step, uint32_t tag, cudaStream_t st) {
+                      uint64_t half_step, uint32_t tag, cudaStream_t st, bool broadcast_u, float* probs_out) {
   if (B == 0) return 0;
   DrawCtx ctx = make_draw_ctx(seed, half_step, tag);
   switch (mode) {
-    case RBM_B200_MODE_SAMPLE: return launch_half_step<RBM_B200_MODE_SAMPLE>(p, direction, in, out, B, U, ctx, chain_offset, st);
-    case RBM_B200_MODE_INJECTED: return launch_half_step<RBM_B200_MODE_INJECTED>(p, direction, in, out, B, U, ctx, chain_offset, st);
+    case RBM_B200_MODE_SAMPLE: return launch_half_step<RBM_B200_MODE_SAMPLE>(p, direction, in, out, B, U, ctx, chain_offset, st, false, probs_out);
+    case RBM_B200_MODE_INJECTED: return launch_half_step<RBM_B200_MODE_INJECTED>(p, direction, in, out, B, U, ctx, chain_offset, st, broadcast_u, probs_out);
     case RBM_B200_MODE_PROBS: return launch_half_step<RBM_B200_MODE_PROBS>(p, direction, in, out, B, U, ctx, chain_offset, st);
   }
   set_error("unknown half-step mode %d", mode);
@@ -334,6 +345,125 @@ int general_negative_phase(const float* v, const float* h, int64_t B, int nV, in
   if (rc) return rc;
   // raw sums are exact integers for binary states; scale once at the end
   return stats_scale(S_vh, S_v, S_h, nV, nH, scale, st);
+}
+
+// ------------------------------------------------------------------------------- CD-k update
+// dW <- momentum * dW + (v0^T h0 - pv^T ph) - W * weight_cost;  W <- W + lr * dW
+// (sandbox/rbm_standalone.py:86,91,95-103,113).  One 64x64 tile of W per CTA, the batch reduced inside
+// the CTA in a fixed order: deterministic, no atomics.
+__global__ void __launch_bounds__(256)
+cd_weight_update_kernel(const float* __restrict__ v0, const float* __restrict__ h0, const float* __restrict__ pv,
+                        const float* __restrict__ ph, int64_t B, int nV, int nH, float* __restrict__ W,
+                        float* __restrict__ dW, float lr, float momentum, float weight_cost) {
+  __shared__ float Vs[GBK][GBM + 4], Hs[GBK][GBN + 4], PVs[GBK][GBM + 4], PHs[GBK][GBN + 4];
+  const int i0 = blockIdx.x * GBM, j0 = blockIdx.y * GBN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4] = {};
+  for (int64_t b0 = 0; b0 < B; b0 += GBK) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int idx = tid + l * 256;
+      const int kk = idx >> 6, n = idx & 63;
+      const int64_t b = b0 + kk;
+      const bool vi = b < B && i0 + n < nV, hj = b < B && j0 + n < nH;
+      Vs[kk][n] = vi ? v0[b * nV + i0 + n] : 0.f;
+      PVs[kk][n] = vi ? pv[b * nV + i0 + n] : 0.f;
+      Hs[kk][n] = hj ? h0[b * nH + j0 + n] : 0.f;
+      PHs[kk][n] = hj ? ph[b * nH + j0 + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GBK; ++kk) {
+      float a[4], bb[4], pa[4], pb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = Vs[kk][ty * 4 + i]; pa[i] = PVs[kk][ty * 4 + i]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { bb[j] = Hs[kk][tx * 4 + j]; pb[j] = PHs[kk][tx * 4 + j]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], fmaf(-pa[i], pb[j], acc[i][j]));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = i0 + ty * 4 + i, c = j0 + tx * 4 + j;
+      if (r < nV && c < nH) {
+        const int64_t idx = (int64_t)r * nH + c;
+        const float w = W[idx];
+        const float u = dW[idx] * momentum + acc[i][j] - w * weight_cost;
+        dW[idx] = u;
+        W[idx] = w + u * lr;
+      }
+    }
+}
+
+// bias updates (rbm_standalone.py:105-115) and the summed squared reconstruction error (:119-120):
+//   x = data side, y = reconstruction side; db <- momentum*db + sum_b (x - y); bias += lr*db
+__global__ void cd_bias_update_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t B, int n,
+                                      float* __restrict__ bias, float* __restrict__ db, float lr, float momentum,
+                                      float* __restrict__ loss) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  float s = 0.f, sq = 0.f;
+  if (c < n) {
+#pragma unroll 8
+    for (int64_t b = 0; b < B; ++b) {
+      const float d = x[b * n + c] - y[b * n + c];
+      s += d;
+      sq = fmaf(d, d, sq);
+    }
+    const float u = db[c] * momentum + s;
+    db[c] = u;
+    bias[c] += u * lr;
+  }
+  if (loss) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if ((threadIdx.x & 31) == 0 && sq != 0.f) atomicAdd(loss, sq);
+  }
+}
+
+size_t general_cd_workspace(int nV, int nH, int64_t B) {
+  return sizeof(float) * (size_t)B * (size_t)(4 * nH + nV);
+}
+
+// One CD-k update (sandbox/rbm_standalone.py:75-121), 3k + 4 launches, everything in fp32.
+int general_cd_step(float* W, float* a, float* c, float* dW, float* da, float* dc, int nV, int nH, const float* v0,
+                    int64_t B, int k, float lr, float momentum, float weight_cost, const float* uniforms,
+                    uint64_t seed, uint64_t draw_offset, float* loss, float* ws, cudaStream_t st) {
+  float* ph0 = ws;
+  float* h0 = ph0 + (size_t)B * nH;
+  float* hcur = h0 + (size_t)B * nH;
+  float* ph = hcur + (size_t)B * nH;
+  float* pv = ph + (size_t)B * nH;
+  rbm_b200_params p{};
+  p.n_visible = nV; p.n_hidden = nH; p.W = W; p.vbias = a; p.hbias = c;
+  int rc;
+  const int draw_mode = uniforms ? RBM_B200_MODE_INJECTED : RBM_B200_MODE_SAMPLE;
+  auto u_row = [&](int i) { return uniforms ? uniforms + (size_t)i * nH : nullptr; };
+  // positive phase: ph0 = sigma(v0 W + c);  h0 = (ph0 >= u_0)                              :79-84
+  // (one kernel: the draw and the probabilities come from the same pre-activation)
+  if ((rc = general_half_step(&p, 0, v0, h0, B, draw_mode, u_row(0), seed, 0, draw_offset, TAG_GIBBS, st, true, ph0))) return rc;
+  // negative phase: k x { pv = sigma(h W^T + a); ph = sigma(pv W + c); h = (ph >= u_{s+1}) }   :66-73
+  const float* hin = h0;
+  for (int s = 0; s < k; ++s) {
+    if ((rc = general_half_step(&p, 1, hin, pv, B, RBM_B200_MODE_PROBS, nullptr, 0, 0, 0, TAG_GIBBS, st, false))) return rc;
+    if ((rc = general_half_step(&p, 0, pv, ph, B, RBM_B200_MODE_PROBS, nullptr, 0, 0, 0, TAG_GIBBS, st, false))) return rc;
+    if (s + 1 < k) {  // the draw after the last sweep is discarded by the reference
+      if ((rc = general_half_step(&p, 0, pv, hcur, B, draw_mode, u_row(s + 1), seed, 0, draw_offset + s + 1, TAG_GIBBS, st, true))) return rc;
+      hin = hcur;
+    }
+  }
+  // updates: all statistics above were taken with the OLD parameters                           :95-120
+  RBM_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  dim3 grid((unsigned)ceil_div(nV, GBM), (unsigned)ceil_div(nH, GBN));
+  cd_weight_update_kernel<<<grid, 256, 0, st>>>(v0, h0, pv, ph, B, nV, nH, W, dW, lr, momentum, weight_cost);
+  cd_bias_update_kernel<<<ceil_div(nV, 128), 128, 0, st>>>(v0, pv, B, nV, a, da, lr, momentum, loss);
+  cd_bias_update_kernel<<<ceil_div(nH, 128), 128, 0, st>>>(ph0, ph, B, nH, c, dc, lr, momentum, nullptr);
+  return check_launch("cd update kernels");
 }
 
 }  // namespace rbm

@@ -11,7 +11,12 @@ namespace rbm {
 // gibbs_general.cu
 int general_half_step(const rbm_b200_params* p, int direction, const float* in, float* out, int64_t B,
                       int mode, const float* U, uint64_t seed, uint64_t chain_offset,
-                      uint64_t half_step, uint32_t tag, cudaStream_t st);
+                      uint64_t half_step, uint32_t tag, cudaStream_t st, bool broadcast_u = false,
+                      float* probs_out = nullptr);
+size_t general_cd_workspace(int nV, int nH, int64_t B);
+int general_cd_step(float* W, float* a, float* c, float* dW, float* da, float* dc, int nV, int nH, const float* v0,
+                    int64_t B, int k, float lr, float momentum, float weight_cost, const float* uniforms,
+                    uint64_t seed, uint64_t draw_offset, float* loss, float* ws, cudaStream_t st);
 int general_init_chains(float* v, int64_t B, int nV, uint64_t seed, uint64_t chain_offset,
                         uint64_t step_offset, cudaStream_t st);
 int general_energy(const rbm_b200_params* p, const float* v, const float* h, float* E, int64_t B,

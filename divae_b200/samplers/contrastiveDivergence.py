@@ -60,6 +60,7 @@ class ContrastiveDivergence(object):
         self._draws = 0
         self._pack = _ops.ParamPack()
         self._view = _Params(self)
+        self._ws = None
 
     def _packed(self):
         # tensors are updated in place, so bump the cache key by hand
@@ -92,28 +93,31 @@ class ContrastiveDivergence(object):
         return probabilities_visible, probabilities_hidden
 
     def contrastive_divergence(self, input_data, uniforms=None):
-        """One CD-k update (rbm_standalone.py:75-121). Returns the summed squared reconstruction error."""
+        """One CD-k update (rbm_standalone.py:75-121) as ONE library call (rbm_b200_cd_step).
+        Returns the summed squared reconstruction error (a 0-d tensor on the device)."""
+        import ctypes
         _lib.require_cuda(input_data, "input data")
-        with torch.no_grad():
-            v0 = input_data.float().contiguous()
-            probabilities_hidden_pos = self.sample_from_hidden(v0)                                   # :79
-            output_hidden_pos = self._draw_hidden(v0, None if uniforms is None else uniforms[0])     # :84
-            associations_pos, sum_v0, _ = _ops.negative_phase_stats(v0, output_hidden_pos, scale=1.0)  # :86
-            probabilities_visible_neg, probabilities_hidden_neg = self.gibbs_sampling(
-                output_hidden_pos, None if uniforms is None else uniforms[1:])
-            associations_neg, sum_pv, sum_ph = _ops.negative_phase_stats(probabilities_visible_neg,
-                                                                         probabilities_hidden_neg, scale=1.0)  # :91
-            sum_ph0 = probabilities_hidden_pos.sum(0)
-            # parameter update (rbm_standalone.py:95-115)
-            self.weights_update *= self.momentum_coefficient
-            self.weights_update += (associations_pos - associations_neg)
-            self.weights_update -= self._weights * self.weight_cost
-            self.visible_bias_update *= self.momentum_coefficient
-            self.visible_bias_update += sum_v0 - sum_pv
-            self.hidden_bias_update *= self.momentum_coefficient
-            self.hidden_bias_update += sum_ph0 - sum_ph
-            self._weights += self.weights_update * self.learning_rate
-            self._visible_bias += self.visible_bias_update * self.learning_rate
-            self._hidden_bias += self.hidden_bias_update * self.learning_rate
-            loss = ((v0 - probabilities_visible_neg) ** 2).sum()                                      # :119-120
+        lib = _lib.load()
+        v0 = input_data.float().contiguous()
+        B = v0.shape[0]
+        if v0.dim() != 2 or v0.shape[1] != self.n_visible:
+            raise RuntimeError("size mismatch: data %s for %d visible units" % (tuple(v0.shape), self.n_visible))
+        k = int(self.n_gibbs_sampling_steps)
+        u = None
+        if uniforms is not None:
+            u = _ops._f32c(uniforms, "uniforms")
+            if u.shape != (k + 1, self.n_hidden):
+                raise RuntimeError("uniforms must be [k+1, n_hidden] = [%d, %d]" % (k + 1, self.n_hidden))
+        nbytes = lib.rbm_b200_cd_workspace(self.n_visible, self.n_hidden, B)
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != v0.device:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=v0.device)
+        loss = torch.empty((), dtype=torch.float32, device=v0.device)
+        with torch.no_grad(), _ops._on_device(v0.device):
+            _lib.check(lib.rbm_b200_cd_step(
+                _ops._ptr(self._weights), _ops._ptr(self._visible_bias), _ops._ptr(self._hidden_bias),
+                _ops._ptr(self.weights_update), _ops._ptr(self.visible_bias_update), _ops._ptr(self.hidden_bias_update),
+                self.n_visible, self.n_hidden, _ops._ptr(v0), B, k, float(self.learning_rate),
+                float(self.momentum_coefficient), float(self.weight_cost), _ops._ptr(u), self._seed, self._draws,
+                _ops._ptr(loss), _ops._ptr(self._ws), nbytes, _ops._stream()), "cd_step")
+        self._draws += k
         return loss

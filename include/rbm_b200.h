@@ -166,6 +166,23 @@ RBM_B200_API int rbm_b200_block_gibbs_stats(const rbm_b200_params *p, float *v, 
                                             size_t workspace_bytes, float scale, float *S_vh, float *S_v,
                                             float *S_h, void *stream);
 
+/* One CD-k parameter update of a vanilla RBM, in place: Contrastive_Divergence.contrastive_divergence
+ * (sandbox/rbm_standalone.py:66-121; the in-tree models/samplers/contrastiveDivergence.py does not parse).
+ *   ph0 = sigma(v0 W + c); h0 = (ph0 >= u_0); k x { pv = sigma(h W^T + a); ph = sigma(pv W + c); h = (ph >= u_s) }
+ *   dW <- momentum dW + (v0^T h0 - pv^T ph) - weight_cost W;  W += lr dW;  biases likewise with
+ *   sum_b (v0 - pv) and sum_b (ph0 - ph);  *loss = sum (v0 - pv)^2.   All fp32 (pv, ph are probabilities).
+ *   uniforms  NULL: independent Philox draws per unit and chain (draw counters draw_offset .. +k-1);
+ *             else [k+1, n_hidden] fp32 rows, each broadcast over the batch like the reference's
+ *             torch.rand(n_hidden) (rbm_standalone.py:72,84).
+ *   W, vbias, hbias, dW, dvb, dhb  updated in place;  loss: device scalar;  k >= 1.
+ * workspace: rbm_b200_cd_workspace(...) bytes. */
+RBM_B200_API size_t rbm_b200_cd_workspace(int32_t n_visible, int32_t n_hidden, int64_t B);
+RBM_B200_API int rbm_b200_cd_step(float *W, float *vbias, float *hbias, float *dW, float *dvb, float *dhb,
+                                  int32_t n_visible, int32_t n_hidden, const float *v0, int64_t B, int32_t k,
+                                  float learning_rate, float momentum, float weight_cost, const float *uniforms,
+                                  uint64_t seed, uint64_t draw_offset, float *loss, void *workspace,
+                                  size_t workspace_bytes, void *stream);
+
 /* Annealed importance sampling of log Z (Salakhutdinov & Murray 2008, RBM form).  The
  * reference has NO estimator: RBM.get_logZ_value returns the literal 33.65
  * (models/rbm/rbm.py:51-54); this entry supplies the missing computation.
