@@ -78,9 +78,9 @@ static int require_device() {
 
 // Shape-based kernel selection (one CUDA library, no backend dispatch).  Measured on B200
 // (profiles/r01_all_configs_1gpu.jsonl): the persistent shared-memory kernel wins for priors up to
-// 128 units per side at any chain count (64x64: 7.2e11 vs 3.0e11 unit-updates/s) and for up to
-// 256 units when chains are few (256x256 x 1024 chains: 0.20 ms vs 0.54 ms per call); with many
-// chains the tcgen05 GEMM wins at 256 units (6.9e11 vs 3.1e11).
+// 128 units per side at any chain count (64x64: 9.0e11 vs 3.0e11 unit-updates/s) and for up to
+// 256 units when chains are few (256x256 x 1024 chains: 0.11 ms vs 0.54 ms per call); with many
+// chains the tcgen05 GEMM wins at 256 units (7.0e11 vs 5.6e11).
 int pick_variant(const rbm_b200_params* p, int64_t B, int variant) {
   if (variant != RBM_B200_VARIANT_AUTO) return variant;
   const int nmax = p->n_visible > p->n_hidden ? p->n_visible : p->n_hidden;
