@@ -28,6 +28,7 @@ namespace {
 
 constexpr int kMaxUnits = 256;
 constexpr int kMaxWords = kMaxUnits / 64;
+constexpr int kSlots = 2 * kMaxWords;       // state slots per side: words, or half-words in HALF mode
 constexpr float kNegLog2e = -1.4426950408889634f;
 
 struct SmemArgs {
@@ -100,7 +101,10 @@ __device__ __forceinline__ int state_bit(int j, int rowhalf, int e) { return 4 *
 //   TRANS_B = true : h -> v, Wop[k][n] = W[n][k]   (ldmatrix on rows n)
 // FULL: both sides are whole 64-unit words (k_tiles == 4*MAXW, every word has 4 live column pairs):
 // all tile guards fold away, leaving a branch-free ldmatrix/mma loop.
-template <int MAXW, bool TRANS_B, bool FULL>
+// HALF (needs FULL): the team has twice as many warps as the side has words; a warp owns HALF-words
+// (32 units = one Philox group).  [ow_begin, ow_end) then counts half-words and the state buffers hold
+// one slot per half-word (bits of the other half are zero), OR-ed together by the reader.
+template <int MAXW, bool TRANS_B, bool FULL, bool HALF>
 __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words, uint32_t* __restrict__ out_words,
                                           int k_tiles, int n_units, int ow_begin, int ow_end, uint32_t w_smem,
                                           int ldw_bytes, const float* __restrict__ nbias, const DrawCtx ctx,
@@ -110,7 +114,8 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
   uint32_t a[MAXW * 4][4];
 #pragma unroll
   for (int w = 0; w < MAXW; ++w) {
-    const uint32_t word = (FULL || w * 4 < k_tiles) ? in_words[w * 32 + lane] : 0u;
+    const uint32_t word = HALF ? (in_words[(2 * w) * 32 + lane] | in_words[(2 * w + 1) * 32 + lane])
+                               : ((FULL || w * 4 < k_tiles) ? in_words[w * 32 + lane] : 0u);
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -123,19 +128,23 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
   const int lrow = TRANS_B ? ((m >> 1) * 8 + rr) : ((m & 1) * 8 + rr);
   const int lcol = TRANS_B ? ((m & 1) * 8) : ((m >> 1) * 8);
 
-  for (int ow = ow_begin; ow < ow_end; ++ow) {
+  constexpr int NP = HALF ? 2 : 4;          // 16-unit column pairs per pass
+  for (int oi = ow_begin; oi < ow_end; ++oi) {
+    const int ow = HALF ? (oi >> 1) : oi;
+    const int hsel = HALF ? (oi & 1) : 0;   // which half of the word this pass covers (HALF only)
     const int n_base = ow * 64;
     const int n_tiles16 = FULL ? 4 : min(4, (n_units - n_base + 15) >> 4);  // live 16-unit column pairs in this word
-    float acc[8][4];
+    float acc[2 * NP][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 2 * NP; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
 #pragma unroll
     for (int kt = 0; kt < MAXW * 4; ++kt) {
       if (FULL || kt < k_tiles) {
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {       // 16-unit column pair p -> n-tiles 2p, 2p+1
+        for (int pi = 0; pi < NP; ++pi) {       // 16-unit column pair p -> n-tiles 2p, 2p+1
+          const int p = HALF ? 2 * hsel + pi : pi;
           if (FULL || p < n_tiles16) {
             uint32_t b0, b1, b2, b3;
             const int row = TRANS_B ? (n_base + p * 16 + lrow) : (kt * 16 + lrow);
@@ -143,16 +152,17 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
             const uint32_t addr = w_smem + (uint32_t)(row * ldw_bytes + col * 2);
             if (TRANS_B) ldmatrix_x4(addr, b0, b1, b2, b3);
             else ldmatrix_x4_trans(addr, b0, b1, b2, b3);
-            mma_bf16_16816(acc[2 * p], a[kt], b0, b1);
-            mma_bf16_16816(acc[2 * p + 1], a[kt], b2, b3);
+            mma_bf16_16816(acc[2 * pi], a[kt], b0, b1);
+            mma_bf16_16816(acc[2 * pi + 1], a[kt], b2, b3);
           }
         }
       }
     }
-    // epilogue: 2 halves of 32 units; per half one Philox call per owned row
+    // epilogue: halves of 32 units; per half one Philox call per owned row
     uint32_t word = 0;
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
+    for (int hfi = 0; hfi < (HALF ? 1 : 2); ++hfi) {
+      const int hf = HALF ? hsel : hfi;
       if (FULL || hf * 2 < n_tiles16) {
         const uint32_t blk = (uint32_t)((ow * 2 + hf) * 4 + t);
         const uint4 x0 = draw_block(ctx, blk, chain_lo);
@@ -170,7 +180,7 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
             const uint32_t wd = rowhalf ? whi[jj] : wlo[jj];
             const uint32_t mbits = e ? __byte_perm(wd, 0x4B000000u, 0x7632) : __byte_perm(wd, 0x4B000000u, 0x7610);
             const float kf = __uint_as_float(mbits) - 8388608.0f;
-            const float s = 1.0f + ex2_approx(fmaf(acc[j][i], kNegLog2e, e ? nb.y : nb.x));
+            const float s = 1.0f + ex2_approx(fmaf(acc[HALF ? jj : j][i], kNegLog2e, e ? nb.y : nb.x));
             const float d = fmaf(-kf, s, 65536.0f);
             amb = amb || (__float_as_uint(d) < __float_as_uint(s));
             word |= (d >= s) ? (1u << state_bit(j, rowhalf, e)) : 0u;
@@ -185,7 +195,7 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
               const int e = i & 1, rowhalf = i >> 1;
               const uint32_t wd = rowhalf ? whi[jj] : wlo[jj];
               const uint32_t k16 = e ? (wd >> 16) : (wd & 0xFFFFu);
-              const uint32_t one = smem_resolve_exact(acc[j][i], nbias[n_base + 8 * j + 2 * t + e], k16, ctx, blk,
+              const uint32_t one = smem_resolve_exact(acc[HALF ? jj : j][i], nbias[n_base + 8 * j + 2 * t + e], k16, ctx, blk,
                                                       rowhalf ? chain_hi : chain_lo, (uint32_t)(2 * jj + e));
               const uint32_t bit = 1u << state_bit(j, rowhalf, e);
               word = one ? (word | bit) : (word & ~bit);
@@ -202,11 +212,11 @@ __device__ __forceinline__ void half_step(const uint32_t* __restrict__ in_words,
         for (int e = 0; e < 2; ++e)
           if (n_base + 8 * j + 2 * t + e >= n_units) word &= ~((1u << state_bit(j, 0, e)) | (1u << state_bit(j, 1, e)));
     }
-    out_words[ow * 32 + lane] = word;
+    out_words[oi * 32 + lane] = word;
   }
 }
 
-template <int MAXW, bool FULL>
+template <int MAXW, bool FULL, bool HALF>
 __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int nV = args.nV, nH = args.nH;
@@ -216,10 +226,10 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
   __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(smem);
   float* nbh = reinterpret_cast<float*>(smem + (size_t)nVp * ldw_bytes);
   float* nbv = nbh + kMaxUnits;
-  uint32_t* vbits = reinterpret_cast<uint32_t*>(nbv + kMaxUnits);   // [groups][kMaxWords][32]
-  uint32_t* hbits = vbits + args.groups * kMaxWords * 32;
+  uint32_t* vbits = reinterpret_cast<uint32_t*>(nbv + kMaxUnits);   // [groups][kSlots][32]
+  uint32_t* hbits = vbits + args.groups * kSlots * 32;
   // fused statistics (S_vh != nullptr): CTA accumulator [64][64] + column sums, per-warp bf16 tiles
-  float* S_s = reinterpret_cast<float*>(hbits + args.groups * kMaxWords * 32);
+  float* S_s = reinterpret_cast<float*>(hbits + args.groups * kSlots * 32);
   float* sv_s = S_s + 64 * 64;
   float* sh_s = sv_s + 64;
   __nv_bfloat16* stat_tiles = reinterpret_cast<__nv_bfloat16*>(sh_s + 64);   // [groups][2][16][kStatLd]
@@ -266,12 +276,14 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
   const int vwords = (nV + 63) >> 6, hwords = (nH + 63) >> 6;
   const int vt = (nV + 15) >> 4, ht = (nH + 15) >> 4;  // k-tiles per side
   // split of output words among the team
-  const int h_per = (hwords + wn - 1) / wn, v_per = (vwords + wn - 1) / wn;
-  const int h_begin = min(hwords, wsub * h_per), h_end = min(hwords, h_begin + h_per);
-  const int v_begin = min(vwords, wsub * v_per), v_end = min(vwords, v_begin + v_per);
+  // ownership in words, or in half-words when HALF
+  const int h_own = HALF ? 2 * hwords : hwords, v_own = HALF ? 2 * vwords : vwords;
+  const int h_per = (h_own + wn - 1) / wn, v_per = (v_own + wn - 1) / wn;
+  const int h_begin = min(h_own, wsub * h_per), h_end = min(h_own, h_begin + h_per);
+  const int v_begin = min(v_own, wsub * v_per), v_end = min(v_own, v_begin + v_per);
   const uint32_t w_smem = (uint32_t)__cvta_generic_to_shared(Ws);
-  uint32_t* myv = vbits + grp * kMaxWords * 32;
-  uint32_t* myh = hbits + grp * kMaxWords * 32;
+  uint32_t* myv = vbits + grp * kSlots * 32;
+  uint32_t* myh = hbits + grp * kSlots * 32;
   const int bar_id = 1 + grp, bar_threads = 32 * wn;
 
   for (int64_t batch = blockIdx.x; batch < args.n_batches; batch += gridDim.x) {
@@ -281,12 +293,13 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
       const uint32_t chain_lo = (uint32_t)(args.chain_offset + (uint64_t)r_lo);
       const uint32_t chain_hi = (uint32_t)(args.chain_offset + (uint64_t)r_hi);
       // ---- initial visible state -> bits (this warp's share of the words)
-      for (int ow = v_begin; ow < v_end; ++ow) {
+      for (int oi = v_begin; oi < v_end; ++oi) {
+        const int ow = HALF ? (oi >> 1) : oi;
+        const int hf_lo = HALF ? (oi & 1) : 0, hf_hi = HALF ? (oi & 1) + 1 : 2;
         uint32_t word = 0;
         if (args.init_chains) {
           const DrawCtx ictx = make_draw_ctx(args.seed, args.step_offset, TAG_INIT);
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
+          for (int hf = hf_lo; hf < hf_hi; ++hf) {
             const uint32_t blk = (uint32_t)((ow * 2 + hf) * 4 + t);
             const uint4 x0 = draw_block(ictx, blk, chain_lo);
             const uint4 x1 = draw_block(ictx, blk, chain_hi);
@@ -303,8 +316,7 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
               }
           }
         } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 4 * hf_lo; j < 4 * hf_hi; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int e = i & 1, rowhalf = i >> 1;
@@ -313,16 +325,16 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
               if (unit < nV && r < args.B && args.v[r * nV + unit] > 0.5f) word |= 1u << state_bit(j, rowhalf, e);
             }
         }
-        myv[ow * 32 + lane] = word;
+        myv[oi * 32 + lane] = word;
       }
       group_barrier(bar_id, bar_threads);
       // ---- 2k half-steps, all on chip
       for (int s = 0; s < args.k; ++s) {
         const DrawCtx ch = make_draw_ctx(args.seed, args.step_offset + 2ull * s, TAG_GIBBS);
-        half_step<MAXW, false, FULL>(myv, myh, vt, nH, h_begin, h_end, w_smem, ldw_bytes, nbh, ch, chain_lo, chain_hi, lane);
+        half_step<MAXW, false, FULL, HALF>(myv, myh, vt, nH, h_begin, h_end, w_smem, ldw_bytes, nbh, ch, chain_lo, chain_hi, lane);
         group_barrier(bar_id, bar_threads);
         const DrawCtx cv = make_draw_ctx(args.seed, args.step_offset + 2ull * s + 1, TAG_GIBBS);
-        half_step<MAXW, true, FULL>(myh, myv, ht, nV, v_begin, v_end, w_smem, ldw_bytes, nbv, cv, chain_lo, chain_hi, lane);
+        half_step<MAXW, true, FULL, HALF>(myh, myv, ht, nV, v_begin, v_end, w_smem, ldw_bytes, nbv, cv, chain_lo, chain_hi, lane);
         group_barrier(bar_id, bar_threads);
       }
       // ---- final states back to the reference's dtype (fp32 {0,1})
@@ -332,10 +344,10 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
         const int n = side ? nH : nV;
         const int wb = side ? h_begin : v_begin, we = side ? h_end : v_end;
         if (side == 1 && args.k == 0) continue;
-        for (int ow = wb; ow < we; ++ow) {
-          const uint32_t word = bits[ow * 32 + lane];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
+        for (int oi = wb; oi < we; ++oi) {
+          const int ow = HALF ? (oi >> 1) : oi;
+          const uint32_t word = bits[oi * 32 + lane];
+          for (int j = HALF ? 4 * (oi & 1) : 0; j < (HALF ? 4 * (oi & 1) + 4 : 8); ++j)
 #pragma unroll
             for (int rowhalf = 0; rowhalf < 2; ++rowhalf) {
               const int64_t r = rowhalf ? r_hi : r_lo;
@@ -428,7 +440,7 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
 
 size_t smem_bytes_needed(int nV, int nH, int groups, bool fuse_stats) {
   const int nVp = round_up(nV, 16), nHp = round_up(nH, 16);
-  size_t n = (size_t)nVp * (nHp + 8) * 2 + 2 * kMaxUnits * sizeof(float) + (size_t)2 * groups * kMaxWords * 32 * sizeof(uint32_t);
+  size_t n = (size_t)nVp * (nHp + 8) * 2 + 2 * kMaxUnits * sizeof(float) + (size_t)2 * groups * kSlots * 32 * sizeof(uint32_t);
   if (fuse_stats) n += (64 * 64 + 128) * sizeof(float) + (size_t)groups * 2 * 16 * kStatLd * 2;
   return n;
 }
@@ -464,6 +476,12 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   int wn = 1;
   const int wn_cap = std::min(vwords, hwords);
   while (wn * 2 <= wn_cap && wn * 2 <= 4 && n_groups * wn < (int64_t)sm_count * 8) wn *= 2;
+  // whole-word square-ish priors (64, 128, 192, 256 units on both sides with equal word counts) take the
+  // guard-free instantiation
+  const bool full = (a.nV % 64 == 0) && (a.nH % 64 == 0) && vwords == hwords && (vwords == 1 || vwords == 2 || vwords == 4);
+  // very few chains: split words in halves over twice the warps (one Philox group per warp)
+  bool half = false;
+  if (full && !fuse && wn == vwords && n_groups * wn * 2 <= (int64_t)sm_count * 4) { half = true; wn *= 2; }
   int groups = 8 / wn;
   while (groups > 1 && ceil_div64(n_groups, groups) < sm_count) groups >>= 1;
   a.wn = wn; a.groups = groups;
@@ -477,17 +495,19 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
     kern<<<grid, threads, smem, st>>>(a);
     return check_launch("smem_gibbs_kernel");
   };
-  // whole-word square-ish priors (64, 128, 192, 256 units on both sides with equal word counts) take the
-  // guard-free instantiation
-  const bool full = (a.nV % 64 == 0) && (a.nH % 64 == 0) && vwords == hwords && (vwords == 1 || vwords == 2 || vwords == 4);
-  if (full) {
-    if (maxw == 1) return launch(smem_gibbs_kernel<1, true>);
-    if (maxw == 2) return launch(smem_gibbs_kernel<2, true>);
-    return launch(smem_gibbs_kernel<4, true>);
+  if (half) {
+    if (maxw == 1) return launch(smem_gibbs_kernel<1, true, true>);
+    if (maxw == 2) return launch(smem_gibbs_kernel<2, true, true>);
+    return launch(smem_gibbs_kernel<4, true, true>);
   }
-  if (maxw <= 1) return launch(smem_gibbs_kernel<1, false>);
-  if (maxw <= 2) return launch(smem_gibbs_kernel<2, false>);
-  return launch(smem_gibbs_kernel<4, false>);
+  if (full) {
+    if (maxw == 1) return launch(smem_gibbs_kernel<1, true, false>);
+    if (maxw == 2) return launch(smem_gibbs_kernel<2, true, false>);
+    return launch(smem_gibbs_kernel<4, true, false>);
+  }
+  if (maxw <= 1) return launch(smem_gibbs_kernel<1, false, false>);
+  if (maxw <= 2) return launch(smem_gibbs_kernel<2, false, false>);
+  return launch(smem_gibbs_kernel<4, false, false>);
 }
 
 }  // namespace rbm
