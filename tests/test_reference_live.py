@@ -36,3 +36,42 @@ def test_torch_port_is_bit_identical_to_reference():
     with torch.no_grad():
         pv, ph, _ = port.block_gibbs_sampling(st, torch.from_numpy(W), torch.from_numpy(a), torch.from_numpy(c), 4)
     assert torch.equal(v, pv) and torch.equal(h, ph)
+
+
+def test_reference_gumbolt_builds_on_top_of_the_dropin_classes():
+    """Build container only: the REAL reference GumBolt (models/autoencoders/gumbolt.py, untouched) constructs
+    its prior and sampler from this repo's classes once divae_b200.dropin.install() has run; forward
+    (encoder/decoder, no sampler) runs; the KL term reaches our sampler (which refuses CPU tensors)."""
+    import sys
+    import types
+    import torch
+    _ref_shim.install()
+    saved = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        import divae_b200
+        from divae_b200 import dropin
+        dropin.install()
+        from models.autoencoders.gumbolt import GumBolt          # reference file
+        ns = types.SimpleNamespace
+        cfg = ns(model=ns(n_latent_hierarchy_lvls=2, n_latent_nodes=64, n_encoder_layer_nodes=200, n_encoder_layers=2,
+                          decoder_hidden_nodes=[200, 200], encoder_hidden_nodes=[200, 200], beta_smoothing_fct=5, output_smoothing_fct=8,
+                          activation_fct="relu", model_type="GumBolt"),
+                 engine=ns(weight_decay_factor=1e-4, n_gibbs_sampling_steps=40), sampler=None)
+        model = GumBolt(flat_input_size=[784], train_ds_mean=torch.full((784,), 0.3), activation_fct=torch.nn.ReLU(), cfg=cfg)
+        model.create_networks()
+        assert type(model.prior) is divae_b200.RBM and type(model.sampler) is divae_b200.PCD
+        assert model.prior.weights.shape == (64, 64)                       # discreteVAE.py:121-122
+        assert model.sampler.get_batch_size() == 128 and model.sampler.n_gibbs_sampling_steps == 40   # dvaepp.py:57
+        keys = set(model.state_dict())
+        assert {"prior._weights", "prior._visible_bias", "prior._hidden_bias", "sampler._RBM._weights"} <= keys
+        x = (torch.rand(8, 784) < 0.3).float()
+        out = model(x, is_training=True) if "is_training" in model.forward.__code__.co_varnames else model(x)
+        assert out is not None
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            model.kl_divergence(out.post_logits, out.post_samples)        # gumbolt.py:69-107 -> sampler
+    finally:
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
