@@ -23,7 +23,8 @@
  *
  * Random draws follow the counter-based Philox4x32-10 contract documented in
  * DESIGN.md ("Draw contract") so results do not depend on tiling, kernel variant
- * or GPU count:  counter = (unit_block, chain_id, half_step, tag), key = seed.
+ * or GPU count:  counter = (unit_block, chain_id, half_step, tag), key = seed.  chain_id is the low 32 bits
+ * of (chain_offset + row): draws repeat after 2^32 chains under one seed; half_step is a 48-bit counter.
  */
 #ifndef RBM_B200_H
 #define RBM_B200_H
