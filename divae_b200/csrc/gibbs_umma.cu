@@ -55,6 +55,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
+#ifdef RBM_TRYWAIT_HINT
+    // suspend-time hint: the thread may sleep in hardware up to this many ns before try_wait returns false
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"((uint32_t)RBM_TRYWAIT_HINT)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -62,6 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
   } while (!done);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -384,11 +395,35 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
       const int n_blk = tile % args.n_tiles, m_blk = tile / args.n_tiles;
       const int as = it & 1;
-      mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u);
-      tcgen05_fence_after();
       const int row_base = (m_blk * CTAS + (int)cta_rank) * BLOCK_M + quarter * 32;
       const int row = row_base + lane;
       const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)row);
+      // Philox words of one 32-unit group (slot mapping: philox.cuh).  They do not depend on the accumulator,
+      // so the first group's words are drawn BEFORE waiting for the MMA and the next group's words right
+      // after the current group: the draw latency overlaps the wait / the TMA store.
+      uint32_t w[4][4];
+      auto draw_group = [&](int g) {
+        const uint32_t b0 = (uint32_t)((n_blk * BLOCK_N + cq * kColsPerWarp + g * 32) >> 5) * 4u;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint4 x = draw_block(args.ctx, b0 + b, chain);
+          w[b][0] = x.x; w[b][1] = x.y; w[b][2] = x.z; w[b][3] = x.w;
+        }
+      };
+#ifndef RBM_LATE_PHILOX
+      draw_group(0);
+#endif
+#ifdef RBM_POLL_ONE_LANE
+      if (lane == 0) mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u);
+      __syncwarp();
+#else
+      // all lanes poll: measured 8 % faster than one polling lane + __syncwarp (profiles/r01_pairs_vs_single.txt)
+      mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u);
+#endif
+#ifdef RBM_LATE_PHILOX
+      draw_group(0);
+#endif
+      tcgen05_fence_after();
       float wsum = 0.f;   // EPI_AIS_WEIGHT: this thread's log-weight increment over its columns (log2 units)
 #pragma unroll 1
       for (int g = 0; g < kGroups; ++g) {
@@ -400,13 +435,6 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           // the previous TMA store of this warp must have finished READING the staging box
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
-        }
-        // four Philox calls cover the 32 units of this group (slot mapping: philox.cuh)
-        uint32_t w[4][4];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint4 x = draw_block(args.ctx, blk0 + b, chain);
-          w[b][0] = x.x; w[b][1] = x.y; w[b][2] = x.z; w[b][3] = x.w;
         }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -486,6 +514,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             tma_store_commit();
           }
         }
+        if (g + 1 < kGroups) draw_group(g + 1);
       }
       if (EPI == EPI_AIS_WEIGHT) {
         // exactly one thread owns (row, slot) in a launch: plain read-modify-write, deterministic
