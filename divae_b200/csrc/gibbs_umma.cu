@@ -661,10 +661,16 @@ struct Plan {
   int wpart_ld;              // AIS log-weight partial slots per chain: 4 per hidden-side N tile
 };
 
-int pick_block_n(int n_pad) {
-  // fewest padded columns wins; ties go to the wider tile
+int pick_block_n(int n_pad, int64_t rows_pad) {
+  // fewest padded columns wins; ties go to the wider tile ...
   const int w256 = round_up(n_pad, 256), w128 = round_up(n_pad, 128);
-  return (w128 < w256) ? 128 : 256;
+  if (w128 < w256) return 128;
+  // ... unless 256-wide tiles would leave most SMs idle (few chains): narrower tiles double the CTAs
+  // and halve the per-launch latency (AIS shards of 2048 chains: profiles/r01_ais_config5_scale.jsonl)
+  static const int force = [] { const char* e = getenv("RBM_B200_BLOCK_N"); return e ? atoi(e) : 0; }();
+  if (force == 128 || force == 256) return force;
+  const int64_t tiles256 = (rows_pad / BLOCK_M) * (w256 / 256);
+  return tiles256 < 74 ? 128 : 256;
 }
 
 Plan make_plan(int nV, int nH, int64_t B) {
@@ -672,7 +678,7 @@ Plan make_plan(int nV, int nH, int64_t B) {
   p.nV = nV; p.nH = nH;
   p.nVp = round_up(nV, 64); p.nHp = round_up(nH, 64);
   p.rows_pad = ceil_div64(B, 2 * BLOCK_M) * (2 * BLOCK_M);   // whole CTA-pair tiles (256 chains)
-  p.bn_h = pick_block_n(p.nHp); p.bn_v = pick_block_n(p.nVp);
+  p.bn_h = pick_block_n(p.nHp, p.rows_pad); p.bn_v = pick_block_n(p.nVp, p.rows_pad);
   auto align = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
   size_t o = 0;
   p.off_W = o; o = align(o + (size_t)p.nVp * p.nHp * 2);
