@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -252,6 +253,139 @@ __device__ __noinline__ uint32_t resolve_exact(float arg, uint32_t k16, DrawCtx 
   return ((y - fl) * 65536.0f >= (float)e16) ? 1u : 0u;
 }
 
+// Per-launch epilogue parameters
+struct EpiParams {
+  const float* nbias;  // -log2(e) * bias, zero padded
+  int ldo;             // padded unit count of the destination state
+  int n_valid;         // real unit count
+  DrawCtx ctx;
+  float scale, bmul, ratio;   // annealed flavours (see HalfStepArgs)
+  int debug_mode;
+};
+
+// Epilogue of ONE 128 x BLOCK_N tile for one warp: TMEM -> decisions -> swizzled smem box -> TMA store.
+//   tmem_acc   TMEM address of the accumulator stage (column 0 of the tile, lane 0)
+//   wait_full  blocks until the MMA has completed the accumulator;  release  hands the stage back
+template <int BLOCK_N, int EPI, class WaitFn, class ReleaseFn>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtensorMap* tmap_out, uint32_t tmem_acc,
+                                              int n_blk, int row_base, uint32_t chain, int quarter, int cq, int lane,
+                                              uint32_t stage_warp, float& wsum, WaitFn wait_full, ReleaseFn release) {
+  constexpr int kColsPerWarp = BLOCK_N / kEpiSets;
+  constexpr int kGroups = kColsPerWarp / 32;   // 32-unit Philox groups per warp per tile
+  // staging box of this warp: row `lane` = 64 B, 16-B chunk c stored at c ^ ((lane >> 1) & 3)  (SWIZZLE_64B)
+  const uint32_t stage_row = stage_warp + (uint32_t)lane * 64u;
+  const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+    // Philox words of one 32-unit group (slot mapping: philox.cuh).  They do not depend on the accumulator,
+    // so the first group's words are drawn BEFORE waiting for the MMA and the next group's words right
+    // after the current group: the draw latency overlaps the wait / the TMA store.
+    uint32_t w[4][4];
+    auto draw_group = [&](int g) {
+      const uint32_t b0 = (uint32_t)((n_blk * BLOCK_N + cq * kColsPerWarp + g * 32) >> 5) * 4u;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint4 x = draw_block(ep.ctx, b0 + b, chain);
+        w[b][0] = x.x; w[b][1] = x.y; w[b][2] = x.z; w[b][3] = x.w;
+      }
+    };
+#ifndef RBM_LATE_PHILOX
+    draw_group(0);
+#endif
+    // all lanes poll: measured 8 % faster than one polling lane + __syncwarp (profiles/r01_pairs_vs_single.txt)
+    wait_full();
+#ifdef RBM_LATE_PHILOX
+    draw_group(0);
+#endif
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int g = 0; g < kGroups; ++g) {
+      const int col_in_tile = cq * kColsPerWarp + g * 32;
+      const int col0 = n_blk * BLOCK_N + col_in_tile;
+      const bool live = col0 < ep.ldo;   // tile overhang beyond the padded unit count
+      const uint32_t blk0 = (uint32_t)(col0 >> 5) * 4u;
+      if (live) {
+        // the previous TMA store of this warp must have finished READING the staging box
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[16];
+        tmem_ld16(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(col_in_tile + 16 * hh), r);
+        tmem_ld_wait();
+        if (g == kGroups - 1 && hh == 1) {
+          // all of this warp's TMEM reads for the tile are done: hand the stage back
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) release();
+        }
+        if (!live || ep.debug_mode == 1) continue;
+        uint32_t pk[8];       // 16 units -> 16 bf16 {0,1}, packed in pairs
+        bool amb = false;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 nb4 = __ldg(reinterpret_cast<const float4*>(ep.nbias + col0 + 16 * hh) + q4);
+          const float nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int c16 = 4 * q4 + i4;           // column within this 16-wide half
+            const int cc = 16 * hh + c16;          // column within the 32-group
+            const int b = (cc & 7) >> 1;           // Philox block
+            const int slot = 2 * (cc >> 3) + (cc & 1);
+            const uint32_t word = w[b][slot >> 1];
+            // float(8388608 + k16) with one byte-permute, minus 2^23 -> exact float(k16)
+            const uint32_t mbits = (slot & 1) ? __byte_perm(word, 0x4B000000u, 0x7632) : __byte_perm(word, 0x4B000000u, 0x7610);
+            const float kf = __uint_as_float(mbits) - 8388608.0f;
+            const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbv[i4])
+                                               : fmaf(__uint_as_float(r[c16]), ep.scale, nbv[i4] * ep.bmul);
+            const Decision q = decision_terms(arg, kf);
+            if (EPI == EPI_AIS_WEIGHT) {
+              // log p*_k(v) - log p*_{k-1}(v), hidden-unit term: softplus(b_k x) - softplus(b_{k-1} x),
+              // in log2 units: softplus(bx)/ln2 = -arg + lg2(1 + 2^arg); clamped so 2^arg stays finite
+              const float ak = fminf(arg, 80.0f);
+              const float akm1 = ak * ep.ratio;
+              if (col0 + cc < ep.n_valid)
+                wsum += (akm1 - ak) + lg2_approx(fminf(q.s, 1.2089258e24f)) - lg2_approx(1.0f + ex2_approx(akm1));
+            }
+            const bool one = q.d >= q.s;
+            amb = amb || (__float_as_uint(q.d) < __float_as_uint(q.s));
+            const uint32_t val = (c16 & 1) ? 0x3F800000u : 0x3F80u;   // bf16 1.0 in the high / low half
+            if (c16 & 1) pk[c16 >> 1] |= one ? val : 0u; else pk[c16 >> 1] = one ? val : 0u;
+          }
+        }
+        if (amb) {
+          // some unit of this span needs its refinement bits: redo the span on the exact path
+#pragma unroll
+          for (int c16 = 0; c16 < 16; ++c16) {
+            const int cc = 16 * hh + c16;
+            const int b = (cc & 7) >> 1, slot = 2 * (cc >> 3) + (cc & 1);
+            const uint32_t word = w[b][slot >> 1];
+            const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
+            const float nbx = __ldg(ep.nbias + col0 + cc);
+            const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbx)
+                                               : fmaf(__uint_as_float(r[c16]), ep.scale, nbx * ep.bmul);
+            const uint32_t one = resolve_exact(arg, k16, ep.ctx, blk0 + b, chain, (uint32_t)slot);
+            const uint32_t val = one ? ((c16 & 1) ? 0x3F800000u : 0x3F80u) : 0u;
+            if (c16 & 1) pk[c16 >> 1] |= val; else pk[c16 >> 1] = val;
+          }
+        }
+        // 16 units = 32 B = two 16-B chunks of this chain's row in the staging box
+        st_shared_v4(stage_row + (((uint32_t)(2 * hh) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+        st_shared_v4(stage_row + (((uint32_t)(2 * hh + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+      }
+      if (live && ep.debug_mode != 1) {
+        // generic-proxy writes -> visible to the async proxy, then ONE coalesced TMA store of the
+        // [32 chains x 32 units] box; columns beyond the padded unit count are clipped by TMA
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmap_out, stage_warp, col0, row_base);
+          tma_store_commit();
+        }
+      }
+      if (g + 1 < kGroups) draw_group(g + 1);
+    }
+}
+
 template <int BLOCK_N, bool B_MN_MAJOR, int EPI, int CTAS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -385,12 +519,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     // ================================= epilogue =================================
     const int quarter = warp_idx & 3;            // TMEM lane quarter this warp may access
     const int cq = (warp_idx - 4) >> 2;          // which share of the tile's columns
-    constexpr int kColsPerWarp = BLOCK_N / kEpiSets;
-    constexpr int kGroups = kColsPerWarp / 32;   // 32-unit Philox groups per warp per tile
-    // staging box of this warp: row `lane` = 64 B, 16-B chunk c stored at c ^ ((lane >> 1) & 3)  (SWIZZLE_64B)
     const uint32_t stage_warp = smem_base + L::kStoreOffset + (uint32_t)(warp_idx - 4) * kStoreWarpBytes;
-    const uint32_t stage_row = stage_warp + (uint32_t)lane * 64u;
-    const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++it) {
       const int n_blk = tile % args.n_tiles, m_blk = tile / args.n_tiles;
@@ -398,124 +527,17 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const int row_base = (m_blk * CTAS + (int)cta_rank) * BLOCK_M + quarter * 32;
       const int row = row_base + lane;
       const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)row);
-      // Philox words of one 32-unit group (slot mapping: philox.cuh).  They do not depend on the accumulator,
-      // so the first group's words are drawn BEFORE waiting for the MMA and the next group's words right
-      // after the current group: the draw latency overlaps the wait / the TMA store.
-      uint32_t w[4][4];
-      auto draw_group = [&](int g) {
-        const uint32_t b0 = (uint32_t)((n_blk * BLOCK_N + cq * kColsPerWarp + g * 32) >> 5) * 4u;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint4 x = draw_block(args.ctx, b0 + b, chain);
-          w[b][0] = x.x; w[b][1] = x.y; w[b][2] = x.z; w[b][3] = x.w;
-        }
-      };
-#ifndef RBM_LATE_PHILOX
-      draw_group(0);
-#endif
-#ifdef RBM_POLL_ONE_LANE
-      if (lane == 0) mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u);
-      __syncwarp();
-#else
-      // all lanes poll: measured 8 % faster than one polling lane + __syncwarp (profiles/r01_pairs_vs_single.txt)
-      mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u);
-#endif
-#ifdef RBM_LATE_PHILOX
-      draw_group(0);
-#endif
-      tcgen05_fence_after();
       float wsum = 0.f;   // EPI_AIS_WEIGHT: this thread's log-weight increment over its columns (log2 units)
-#pragma unroll 1
-      for (int g = 0; g < kGroups; ++g) {
-        const int col_in_tile = cq * kColsPerWarp + g * 32;
-        const int col0 = n_blk * BLOCK_N + col_in_tile;
-        const bool live = col0 < args.ldo;   // tile overhang beyond the padded unit count
-        const uint32_t blk0 = (uint32_t)(col0 >> 5) * 4u;
-        if (live) {
-          // the previous TMA store of this warp must have finished READING the staging box
-          if (lane == 0) tma_store_wait_read();
-          __syncwarp();
-        }
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + col_in_tile + 16 * hh), r);
-          tmem_ld_wait();
-          if (g == kGroups - 1 && hh == 1) {
-            // all of this warp's TMEM reads for the tile are done: hand the stage back
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CTAS == 2) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(as), 0));   // the leader's barrier
-              else mbar_arrive(tmem_empty_bar(as));
-            }
-          }
-          if (!live || args.debug_mode == 1) continue;
-          uint32_t pk[8];       // 16 units -> 16 bf16 {0,1}, packed in pairs
-          bool amb = false;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 nb4 = __ldg(reinterpret_cast<const float4*>(args.nbias + col0 + 16 * hh) + q4);
-            const float nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const int c16 = 4 * q4 + i4;           // column within this 16-wide half
-              const int cc = 16 * hh + c16;          // column within the 32-group
-              const int b = (cc & 7) >> 1;           // Philox block
-              const int slot = 2 * (cc >> 3) + (cc & 1);
-              const uint32_t word = w[b][slot >> 1];
-              // float(8388608 + k16) with one byte-permute, minus 2^23 -> exact float(k16)
-              const uint32_t mbits = (slot & 1) ? __byte_perm(word, 0x4B000000u, 0x7632) : __byte_perm(word, 0x4B000000u, 0x7610);
-              const float kf = __uint_as_float(mbits) - 8388608.0f;
-              const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbv[i4])
-                                                 : fmaf(__uint_as_float(r[c16]), args.scale, nbv[i4] * args.bmul);
-              const Decision q = decision_terms(arg, kf);
-              if (EPI == EPI_AIS_WEIGHT) {
-                // log p*_k(v) - log p*_{k-1}(v), hidden-unit term: softplus(b_k x) - softplus(b_{k-1} x),
-                // in log2 units: softplus(bx)/ln2 = -arg + lg2(1 + 2^arg); clamped so 2^arg stays finite
-                const float ak = fminf(arg, 80.0f);
-                const float akm1 = ak * args.ratio;
-                if (col0 + cc < args.n_valid)
-                  wsum += (akm1 - ak) + lg2_approx(fminf(q.s, 1.2089258e24f)) - lg2_approx(1.0f + ex2_approx(akm1));
-              }
-              const bool one = q.d >= q.s;
-              amb = amb || (__float_as_uint(q.d) < __float_as_uint(q.s));
-              const uint32_t val = (c16 & 1) ? 0x3F800000u : 0x3F80u;   // bf16 1.0 in the high / low half
-              if (c16 & 1) pk[c16 >> 1] |= one ? val : 0u; else pk[c16 >> 1] = one ? val : 0u;
-            }
-          }
-          if (amb) {
-            // some unit of this span needs its refinement bits: redo the span on the exact path
-#pragma unroll
-            for (int c16 = 0; c16 < 16; ++c16) {
-              const int cc = 16 * hh + c16;
-              const int b = (cc & 7) >> 1, slot = 2 * (cc >> 3) + (cc & 1);
-              const uint32_t word = w[b][slot >> 1];
-              const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
-              const float nbx = __ldg(args.nbias + col0 + cc);
-              const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbx)
-                                                 : fmaf(__uint_as_float(r[c16]), args.scale, nbx * args.bmul);
-              const uint32_t one = resolve_exact(arg, k16, args.ctx, blk0 + b, chain, (uint32_t)slot);
-              const uint32_t val = one ? ((c16 & 1) ? 0x3F800000u : 0x3F80u) : 0u;
-              if (c16 & 1) pk[c16 >> 1] |= val; else pk[c16 >> 1] = val;
-            }
-          }
-          // 16 units = 32 B = two 16-B chunks of this chain's row in the staging box
-          st_shared_v4(stage_row + (((uint32_t)(2 * hh) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
-          st_shared_v4(stage_row + (((uint32_t)(2 * hh + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
-        }
-        if (live && args.debug_mode != 1) {
-          // generic-proxy writes -> visible to the async proxy, then ONE coalesced TMA store of the
-          // [32 chains x 32 units] box; columns beyond the padded unit count are clipped by TMA
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmap_out, stage_warp, col0, row_base);
-            tma_store_commit();
-          }
-        }
-        if (g + 1 < kGroups) draw_group(g + 1);
-      }
+      EpiParams ep;
+      ep.nbias = args.nbias; ep.ldo = args.ldo; ep.n_valid = args.n_valid; ep.ctx = args.ctx;
+      ep.scale = args.scale; ep.bmul = args.bmul; ep.ratio = args.ratio; ep.debug_mode = args.debug_mode;
+      epilogue_tile<BLOCK_N, EPI>(
+          ep, &tmap_out, tmem_base + (uint32_t)(as * BLOCK_N), n_blk, row_base, chain, quarter, cq, lane, stage_warp, wsum,
+          [&] { mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u); },
+          [&] {
+            if (CTAS == 2) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(as), 0));   // the leader's barrier
+            else mbar_arrive(tmem_empty_bar(as));
+          });
       if (EPI == EPI_AIS_WEIGHT) {
         // exactly one thread owns (row, slot) in a launch: plain read-modify-write, deterministic
         float* slot_ptr = args.wpart + (size_t)row * args.wpart_ld + (n_blk * kEpiSets + cq);
@@ -534,6 +556,171 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-step variant: ALL half-steps of a chain block in ONE launch, for jobs whose per-half-step grid
+// would not fill the GPU (few chains: PCD batches, AIS shards).  A cluster of n_tiles CTAs owns one
+// 128-chain row block for the whole run; CTA `n_blk` computes output tile n_blk of every half-step.
+// Between half-steps only that row block's CTAs have to agree (rows are independent), so the only
+// synchronisation is ONE cluster barrier per half-step after the state tile has been stored - no
+// relaunch, no grid-wide sync, and the draw context / annealing schedule advance in registers.
+struct MultiArgs {
+  const float* nbias[2];   // [dir]: dir 0 = v->h (hidden biases), dir 1 = h->v
+  int ldo[2];              // padded unit count of the state WRITTEN by dir
+  int n_valid[2];
+  int n_tiles[2];
+  int k_blocks[2];
+  int steps;               // number of half-steps in this launch
+  int first_dir;
+  uint64_t seed, chain_offset, step_offset;   // half-step t draws with counter step_offset + t
+  uint32_t tag;
+  const float* betas;      // annealed flavours: beta index of half-step t is 1 + t/2
+  float* wpart;            // AIS: [rows, wpart_ld] log-weight partials (log2 units), added to at the end
+  int wpart_ld;
+};
+
+template <int BLOCK_N, int EPI0, int EPI1>
+__global__ void __launch_bounds__(kNumThreads, 1)
+umma_multistep_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+                      const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ CUtensorMap tm_b1,
+                      const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1,
+                      const MultiArgs args) {
+  using L = SmemLayout<BLOCK_N, 1>;
+  constexpr int kStages = L::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L::kBarOffset;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kBarOffset + 8 * (2 * kStages + 4));
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blk = (int)cluster_ctarank();                     // output tile of this CTA
+  uint32_t cs;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cs));
+  const int m_blk = (int)(blockIdx.x / cs);                      // the cluster's 128-chain row block
+  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;    // one accumulator (steps are serialised)
+
+  if (warp_idx == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_o0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_o1) : "memory");
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp_idx == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int quarter = warp_idx & 3;
+  const int cq = (warp_idx - 4) >> 2;
+  const uint32_t stage_warp = smem_base + L::kStoreOffset + (uint32_t)(warp_idx >= 4 ? warp_idx - 4 : 0) * kStoreWarpBytes;
+  const int row_base = m_blk * BLOCK_M + quarter * 32;
+  const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)(row_base + lane));
+  int stage = 0; uint32_t phase = 0;     // smem ring position (producer lane and MMA lane each keep their own copy)
+  int it = 0;                            // number of tiles this CTA has processed (accumulator barrier parity)
+  float wsum = 0.f;
+
+  for (int t = 0; t < args.steps; ++t) {
+    const int dir = (args.first_dir + t) & 1;
+    const bool active = n_blk < args.n_tiles[dir];
+    if (active) {
+      const CUtensorMap* tm_a = dir ? &tm_a1 : &tm_a0;
+      const CUtensorMap* tm_b = dir ? &tm_b1 : &tm_b0;
+      if (warp_idx == 0) {
+        if (lane == 0) {
+          // ---- TMA producer: this row block's state (A) and tile n_blk of W (B: MN-major for dir 0, K-major for dir 1)
+          for (int kb = 0; kb < args.k_blocks[dir]; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * L::kStageBytes;
+            const uint32_t sb = sa + kABytes;
+            mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
+            tma_load_2d(sa, tm_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+            if (dir == 0) {
+#pragma unroll
+              for (int nb = 0; nb < BLOCK_N / 64; ++nb)
+                tma_load_2d(sb + nb * (BLOCK_K * 128), tm_b, full_bar(stage), n_blk * BLOCK_N + nb * 64, kb * BLOCK_K);
+            } else {
+              tma_load_2d(sb, tm_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      } else if (warp_idx == 1) {
+        if (lane == 0) {
+          // ---- MMA issuer (the accumulator is free: the previous half-step ended with a cluster barrier)
+          const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, dir == 0);
+          for (int kb = 0; kb < args.k_blocks[dir]; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_base + stage * L::kStageBytes;
+            const uint32_t sb = sa + kABytes;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+              const uint64_t bdesc = dir == 0 ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                              : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+              umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(tmem_full_bar);
+        }
+      } else if (warp_idx >= 4) {
+        // ---- epilogue
+        EpiParams ep;
+        ep.nbias = args.nbias[dir]; ep.ldo = args.ldo[dir]; ep.n_valid = args.n_valid[dir];
+        ep.ctx = make_draw_ctx(args.seed, args.step_offset + (uint64_t)t, args.tag);
+        ep.scale = -1.4426950408889634f; ep.bmul = 1.f; ep.ratio = 0.f; ep.debug_mode = 0;
+        if (EPI0 != EPI_GIBBS) {
+          const float bk = __ldg(args.betas + 1 + (t >> 1)), bkm1 = __ldg(args.betas + (t >> 1));
+          ep.scale = -1.4426950408889634f * bk;
+          ep.bmul = dir == 0 ? bk : 1.f;
+          ep.ratio = bkm1 / bk;
+        }
+        auto wait_full = [&] { mbar_wait(tmem_full_bar, (uint32_t)it & 1u); };
+        auto release = [] {};
+        const CUtensorMap* tm_o = dir ? &tm_o1 : &tm_o0;
+        if (dir == 0) epilogue_tile<BLOCK_N, EPI0>(ep, tm_o, tmem_base, n_blk, row_base, chain, quarter, cq, lane, stage_warp, wsum, wait_full, release);
+        else epilogue_tile<BLOCK_N, EPI1>(ep, tm_o, tmem_base, n_blk, row_base, chain, quarter, cq, lane, stage_warp, wsum, wait_full, release);
+        if (lane == 0) tma_store_wait_all();       // this CTA's part of the new state is in global memory
+      }
+      ++it;
+    }
+    // ---- end of the half-step: every CTA of the row block has stored its tile before anyone reads the new state
+    __syncwarp();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  if (EPI0 == EPI_AIS_WEIGHT && warp_idx >= 4 && n_blk < args.n_tiles[0]) {
+    float* slot_ptr = args.wpart + (size_t)(row_base + lane) * args.wpart_ld + (n_blk * kEpiSets + cq);
+    *slot_ptr += wsum;
+  }
+  __syncthreads();
+  if (warp_idx == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -653,11 +840,13 @@ bool pairs_enabled() {
   return on;
 }
 
+constexpr int kMaxDeviceBetas = 1 << 18;   // longer AIS schedules fall back to one launch per half-step
+
 struct Plan {
   int nV, nH, nVp, nHp;      // padded to multiples of 64
   int64_t rows_pad;          // chains padded to a multiple of 256 (one CTA-pair tile)
   int bn_h, bn_v;            // BLOCK_N for the v->h and h->v half-steps
-  size_t off_W, off_nbh, off_nbv, off_V, off_H, off_wpart, total;
+  size_t off_W, off_nbh, off_nbv, off_V, off_H, off_wpart, off_betas, total;
   int wpart_ld;              // AIS log-weight partial slots per chain: 4 per hidden-side N tile
 };
 
@@ -669,8 +858,10 @@ int pick_block_n(int n_pad, int64_t rows_pad) {
   // and halve the per-launch latency (AIS shards of 2048 chains: profiles/r01_ais_config5_scale.jsonl)
   static const int force = [] { const char* e = getenv("RBM_B200_BLOCK_N"); return e ? atoi(e) : 0; }();
   if (force == 128 || force == 256) return force;
+  // (measured, benchmarks/multistep_ab.py: 512x512 -> 128-wide tiles, 7.4 vs 10.7 us per half-step;
+  //  1024x1024 -> 256-wide tiles keep the cluster at 4 CTAs, 13.5 vs 19.9 us)
   const int64_t tiles256 = (rows_pad / BLOCK_M) * (w256 / 256);
-  return tiles256 < 74 ? 128 : 256;
+  return (tiles256 < 74 && n_pad <= 512) ? 128 : 256;
 }
 
 Plan make_plan(int nV, int nH, int64_t B) {
@@ -688,6 +879,7 @@ Plan make_plan(int nV, int nH, int64_t B) {
   p.off_H = o; o = align(o + (size_t)p.rows_pad * p.nHp * 2);
   p.wpart_ld = kEpiSets * ceil_div(p.nHp, p.bn_h);
   p.off_wpart = o; o = align(o + (size_t)p.rows_pad * p.wpart_ld * 4);
+  p.off_betas = o; o = align(o + (size_t)kMaxDeviceBetas * 4);   // AIS schedule for the multi-step kernel
   p.total = o + 1024;  // slack to align the caller's pointer
   return p;
 }
@@ -731,6 +923,37 @@ int launch_half_step(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   if (BLOCK_N == 256 && use_pairs)
     return launch_half_step_impl<256, B_MN_MAJOR, EPI, 2>(ta, tb, to, a, sm_count, st);
   return launch_half_step_impl<BLOCK_N, B_MN_MAJOR, EPI, 1>(ta, tb, to, a, sm_count, st);
+}
+
+// cluster sizes the multi-step kernel is launched with (one CTA per output tile of a row block)
+bool multistep_cluster_ok(int cs) { return cs == 1 || cs == 2 || cs == 4 || cs == 8; }
+
+// -1: automatic (one wave of CTAs), 0: never, 1: whenever the shape allows
+int multistep_mode() {
+  static const int mode = [] { const char* e = getenv("RBM_B200_MULTISTEP"); return e ? atoi(e) : -1; }();
+  return mode;
+}
+
+template <int BLOCK_N, int EPI0, int EPI1>
+int launch_multistep(const CUtensorMap* tm, const MultiArgs& a, int m_tiles, int cs, cudaStream_t st) {
+  auto kern = umma_multistep_kernel<BLOCK_N, EPI0, EPI1>;
+  using L = SmemLayout<BLOCK_N, 1>;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  if ((rc = ensure_dynamic_smem(kern, di.device, L::kTotal))) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(m_tiles * cs));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RBM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a));
+  return check_launch("umma_multistep_kernel");
 }
 
 }  // namespace
@@ -799,6 +1022,35 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   if ((rc = make_tmap(&tm_w_k_single, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, (uint32_t)pl.bn_v))) return rc;
   if ((rc = make_tmap(&tm_w_k_pair, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 128))) return rc;
 
+  // Few chains: one launch for all 2k half-steps (cluster per 128-chain row block, see umma_multistep_kernel)
+  {
+    const int nt_h = ceil_div(pl.nHp, pl.bn_h), nt_v = ceil_div(pl.nVp, pl.bn_v);
+    const int cs = std::max(nt_h, nt_v);
+    const int m_tiles = (int)(pl.rows_pad / BLOCK_M);
+    const int mode = multistep_mode();
+    const bool shape_ok = k >= 1 && pl.bn_h == pl.bn_v && multistep_cluster_ok(cs);
+    if (shape_ok && (mode == 1 || (mode == -1 && (int64_t)m_tiles * cs <= sm_count))) {
+      CUtensorMap tm[6];
+      if ((rc = make_tmap(&tm[0], Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
+      if ((rc = make_tmap(&tm[1], Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
+      tm[2] = tm_w_mn;
+      tm[3] = tm_w_k_single;
+      if ((rc = make_tmap(&tm[4], Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+      if ((rc = make_tmap(&tm[5], Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+      MultiArgs ma{};
+      ma.nbias[0] = nbh; ma.nbias[1] = nbv; ma.ldo[0] = pl.nHp; ma.ldo[1] = pl.nVp;
+      ma.n_valid[0] = pl.nH; ma.n_valid[1] = pl.nV; ma.n_tiles[0] = nt_h; ma.n_tiles[1] = nt_v;
+      ma.k_blocks[0] = pl.nVp / BLOCK_K; ma.k_blocks[1] = pl.nHp / BLOCK_K;
+      ma.steps = 2 * k; ma.first_dir = 0; ma.seed = seed; ma.chain_offset = chain_offset; ma.step_offset = step_offset;
+      ma.tag = TAG_GIBBS;
+      rc = pl.bn_h == 256 ? launch_multistep<256, EPI_GIBBS, EPI_GIBBS>(tm, ma, m_tiles, cs, st)
+                          : launch_multistep<128, EPI_GIBBS, EPI_GIBBS>(tm, ma, m_tiles, cs, st);
+      if (rc) return rc;
+      chunk_rows = pl.rows_pad;
+      goto convert_out;
+    }
+  }
+
   for (int64_t r0 = 0; r0 < pl.rows_pad; r0 += chunk_rows) {
     const int64_t rows = std::min(chunk_rows, pl.rows_pad - r0);
     __nv_bfloat16* Vc = Vs + r0 * pl.nVp;
@@ -831,6 +1083,7 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
       if (rc) return rc;
     }
   }
+convert_out:
   // back to the reference's dtype
   {
     const int64_t nv = B * pl.nV, nh = B * pl.nH;
@@ -905,6 +1158,35 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
   av.n_valid = pl.nV; av.wpart = wpart; av.wpart_ld = pl.wpart_ld;
 
   const int K = n_betas - 1;
+  // Few chains per GPU (e.g. config 5 sharded over 8 GPUs: 2048 chains): the whole schedule in ONE launch
+  {
+    const int nt_h = ceil_div(pl.nHp, pl.bn_h), nt_v = ceil_div(pl.nVp, pl.bn_v);
+    const int cs = std::max(nt_h, nt_v);
+    const int m_tiles = (int)(pl.rows_pad / BLOCK_M);
+    const int mode = multistep_mode();
+    const bool shape_ok = pl.bn_h == pl.bn_v && multistep_cluster_ok(cs) && n_betas <= kMaxDeviceBetas && !pairs;
+    if (shape_ok && (mode == 1 || (mode == -1 && (int64_t)m_tiles * cs <= sm_count))) {
+      float* betas_dev = reinterpret_cast<float*>(base + pl.off_betas);
+      std::vector<float> bf(n_betas);
+      for (int i = 0; i < n_betas; ++i) bf[i] = (float)betas[i];
+      // pageable source: the runtime stages the copy before returning, so `bf` may go out of scope
+      RBM_CUDA_TRY(cudaMemcpyAsync(betas_dev, bf.data(), sizeof(float) * (size_t)n_betas, cudaMemcpyHostToDevice, st));
+      CUtensorMap tm[6];
+      tm[0] = tm_v; tm[1] = tm_h; tm[2] = tm_w_mn; tm[3] = tm_w_k; tm[4] = to_h; tm[5] = to_v;
+      MultiArgs ma{};
+      ma.nbias[0] = nbh; ma.nbias[1] = nbv; ma.ldo[0] = pl.nHp; ma.ldo[1] = pl.nVp;
+      ma.n_valid[0] = pl.nH; ma.n_valid[1] = pl.nV; ma.n_tiles[0] = nt_h; ma.n_tiles[1] = nt_v;
+      ma.k_blocks[0] = pl.nVp / BLOCK_K; ma.k_blocks[1] = pl.nHp / BLOCK_K;
+      ma.steps = 2 * K - 1;            // K hidden steps, K-1 visible steps (the last transition is skipped)
+      ma.first_dir = 0; ma.seed = seed; ma.chain_offset = chain_offset; ma.step_offset = 2;   // half-step counter 2k / 2k+1
+      ma.tag = TAG_AIS; ma.betas = betas_dev; ma.wpart = wpart; ma.wpart_ld = pl.wpart_ld;
+      rc = pl.bn_h == 256 ? launch_multistep<256, EPI_AIS_WEIGHT, EPI_ANNEALED>(tm, ma, m_tiles, cs, st)
+                          : launch_multistep<128, EPI_AIS_WEIGHT, EPI_ANNEALED>(tm, ma, m_tiles, cs, st);
+      if (rc) return rc;
+      ais_reduce_kernel<<<(unsigned)ceil_div64(M, 256), 256, 0, st>>>(wpart, pl.wpart_ld, M, logw);
+      return check_launch("ais_reduce_kernel");
+    }
+  }
   for (int k = 1; k <= K; ++k) {
     const float bk = (float)betas[k], bkm1 = (float)betas[k - 1];
     ah.ctx = make_draw_ctx(seed, 2ull * k, TAG_AIS);
