@@ -42,7 +42,7 @@ PROTOTYPES = {
     "rbm_b200_block_gibbs_workspace": (_sz, [_i32, _i32, _i64, _int]),
     "rbm_b200_block_gibbs": (_int, [_P, _vp, _vp, _i64, _i32, _int, _u64, _u64, _u64, _int, _vp, _sz, _vp]),
     "rbm_b200_block_gibbs_stats": (_int, [_P, _vp, _vp, _i64, _i32, _int, _u64, _u64, _u64, _int, _vp, _sz, _f32, _vp, _vp,
-                                           _vp, _vp]),
+                                           _vp, _vp, _vp]),
     "rbm_b200_block_gibbs_injected": (_int, [_P, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "rbm_b200_meanfield": (_int, [_P, _vp, _vp, _i64, _i32, _vp]),
     "rbm_b200_energy_workspace": (_sz, [_i32, _i32, _i64]),

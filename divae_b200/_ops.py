@@ -197,18 +197,20 @@ class _EnergyExpFromStats(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, W, a, c, S, sv, sh):
+    def forward(ctx, W, a, c, S, sv, sh, value):
         ctx.save_for_backward(S, sv, sh)
-        return -((W * S).sum() + (a * sv).sum() + (c * sh).sum())
+        if value is not None:        # already computed by rbm_b200_block_gibbs_stats
+            return value.clone()
+        return -(torch.dot(W.reshape(-1), S.reshape(-1)) + torch.dot(a, sv) + torch.dot(c, sh))
 
     @staticmethod
     def backward(ctx, g):
         S, sv, sh = ctx.saved_tensors
-        return -g * S, -g * sv, -g * sh, None, None, None
+        return -g * S, -g * sv, -g * sh, None, None, None, None
 
 
-def energy_exp_from_stats(rbm, S, sv, sh):
-    return _EnergyExpFromStats.apply(rbm.weights, rbm.visible_bias, rbm.hidden_bias, S, sv, sh)
+def energy_exp_from_stats(rbm, S, sv, sh, value=None):
+    return _EnergyExpFromStats.apply(rbm.weights, rbm.visible_bias, rbm.hidden_bias, S, sv, sh, value)
 
 
 def energy_exp(rbm, rbm_vis, rbm_hid):

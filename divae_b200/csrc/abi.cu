@@ -201,7 +201,7 @@ int rbm_b200_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B
 int rbm_b200_block_gibbs_stats(const rbm_b200_params* p, float* v, float* h, int64_t B, int32_t k,
                                int init_chains, uint64_t seed, uint64_t chain_offset, uint64_t step_offset,
                                int variant, void* workspace, size_t workspace_bytes, float scale, float* S_vh,
-                               float* S_v, float* S_h, void* stream) {
+                               float* S_v, float* S_h, float* energy_exp, void* stream) {
   RBM_REQUIRE(p != nullptr && S_vh && S_v && S_h, RBM_B200_ERR_INVALID, "NULL statistics pointer");
   RBM_REQUIRE(k >= 1, RBM_B200_ERR_INVALID, "the negative phase needs at least one Gibbs step (h is undefined for k = 0)");
   int rc = require_device();
@@ -212,8 +212,11 @@ int rbm_b200_block_gibbs_stats(const rbm_b200_params* p, float* v, float* h, int
   bool fused = false;
   if ((rc = block_gibbs_impl(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, variant, workspace,
                              workspace_bytes, stream, S_vh, S_v, S_h, &fused))) return rc;
-  if (fused) return stats_scale(S_vh, S_v, S_h, p->n_visible, p->n_hidden, scale, st);
-  return general_negative_phase(v, h, B, p->n_visible, p->n_hidden, scale, S_vh, S_v, S_h, st);
+  if (fused) rc = stats_scale(S_vh, S_v, S_h, p->n_visible, p->n_hidden, scale, st);
+  else rc = general_negative_phase(v, h, B, p->n_visible, p->n_hidden, scale, S_vh, S_v, S_h, st);
+  if (rc || !energy_exp) return rc;
+  RBM_REQUIRE(p->W != nullptr, RBM_B200_ERR_INVALID, "energy_exp needs the fp32 W");
+  return stats_energy(p, S_vh, S_v, S_h, energy_exp, st);
 }
 
 int rbm_b200_block_gibbs_injected(const rbm_b200_params* p, float* v, float* h, int64_t B, int32_t k,

@@ -309,6 +309,35 @@ int general_energy(const rbm_b200_params* p, const float* v, const float* h, flo
   return check_launch("energy_finalize_kernel");
 }
 
+// E = -(<W, S_vh> + a.S_v + c.S_h): the mean energy of the batch whose (scaled) statistics are S_*.
+// One CTA, fixed-order reduction: deterministic.
+__global__ void __launch_bounds__(1024)
+stats_energy_kernel(const float* __restrict__ W, const float* __restrict__ a, const float* __restrict__ c,
+                    const float* __restrict__ S, const float* __restrict__ sv, const float* __restrict__ sh,
+                    int nV, int nH, float* __restrict__ E) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const int64_t n = (int64_t)nV * nH;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(W[i], S[i], s);
+  for (int i = threadIdx.x; i < nV; i += blockDim.x) s = fmaf(a[i], sv[i], s);
+  for (int i = threadIdx.x; i < nH; i += blockDim.x) s = fmaf(c[i], sh[i], s);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (threadIdx.x == 0) *E = -s;
+  }
+}
+
+int stats_energy(const rbm_b200_params* p, const float* S_vh, const float* S_v, const float* S_h, float* E, cudaStream_t st) {
+  stats_energy_kernel<<<1, 1024, 0, st>>>(p->W, p->vbias, p->hbias, S_vh, S_v, S_h, p->n_visible, p->n_hidden, E);
+  return check_launch("stats_energy_kernel");
+}
+
 int stats_zero(float* S_vh, float* S_v, float* S_h, int nV, int nH, cudaStream_t st) {
   const int64_t n = (int64_t)nV * nH + nV + nH;
   stats_scale3_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(S_vh, S_v, S_h, (int64_t)nV * nH, nV, nH, 0.f);

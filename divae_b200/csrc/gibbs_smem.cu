@@ -363,29 +363,38 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
       }
       if (fuse_stats && args.k > 0) {
         // ---- fused negative-phase statistics of this group's final (v, h): S += v^T h, column sums.
-        // (<= 64 units per side => one word per side and one warp per group.)
+        // (<= 64 units per side => one word per side; the group's warps - one, or two in HALF mode - each
+        //  expand the state bits they own into the group's bf16 tiles and split the MMA row tiles.)
         __nv_bfloat16* vs = stat_tiles + (size_t)grp * 2 * 16 * kStatLd;
         __nv_bfloat16* hs = vs + 16 * kStatLd;
-        const uint32_t wv = myv[lane], wh = myh[lane];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
+        const int vj0 = HALF ? 4 * (v_begin & 1) : 0, hj0 = HALF ? 4 * (h_begin & 1) : 0;
+        const int nj = HALF ? 4 : 8;
+        const uint32_t wv = myv[(HALF ? v_begin : 0) * 32 + lane], wh = myh[(HALF ? h_begin : 0) * 32 + lane];
+        for (int jj = 0; jj < nj; ++jj)
 #pragma unroll
           for (int rowhalf = 0; rowhalf < 2; ++rowhalf) {
             const bool valid = (rowhalf ? r_hi : r_lo) < args.B;    // padded chains contribute nothing
-            const int row = g + 8 * rowhalf, col = 8 * j + 2 * t;
-            const uint32_t b0 = state_bit(j, rowhalf, 0), b1 = state_bit(j, rowhalf, 1);
-            const uint32_t pv = valid ? ((((wv >> b0) & 1u) * 0x3F80u) | (((wv >> b1) & 1u) * 0x3F800000u)) : 0u;
-            const uint32_t ph = valid ? ((((wh >> b0) & 1u) * 0x3F80u) | (((wh >> b1) & 1u) * 0x3F800000u)) : 0u;
-            *reinterpret_cast<uint32_t*>(vs + row * kStatLd + col) = pv;
-            *reinterpret_cast<uint32_t*>(hs + row * kStatLd + col) = ph;
+            const int row = g + 8 * rowhalf;
+            {
+              const int j = vj0 + jj;
+              const uint32_t b0 = state_bit(j, rowhalf, 0), b1 = state_bit(j, rowhalf, 1);
+              const uint32_t pv = valid ? ((((wv >> b0) & 1u) * 0x3F80u) | (((wv >> b1) & 1u) * 0x3F800000u)) : 0u;
+              *reinterpret_cast<uint32_t*>(vs + row * kStatLd + 8 * j + 2 * t) = pv;
+            }
+            {
+              const int j = hj0 + jj;
+              const uint32_t b0 = state_bit(j, rowhalf, 0), b1 = state_bit(j, rowhalf, 1);
+              const uint32_t ph = valid ? ((((wh >> b0) & 1u) * 0x3F80u) | (((wh >> b1) & 1u) * 0x3F800000u)) : 0u;
+              *reinterpret_cast<uint32_t*>(hs + row * kStatLd + 8 * j + 2 * t) = ph;
+            }
           }
-        __syncwarp();
+        group_barrier(bar_id, bar_threads);
         const uint32_t vs_a = (uint32_t)__cvta_generic_to_shared(vs), hs_a = (uint32_t)__cvta_generic_to_shared(hs);
         const int m = lane >> 3, rr = lane & 7;
         // A = v^T (m = visible unit, k = chain): x4.trans of [chains 0-7|8-15] x [units 0-7|8-15] blocks
         // B = h   (k = chain, n = hidden unit): x4.trans of the same block shape
 #pragma unroll 1
-        for (int mt = 0; mt < vt; ++mt) {
+        for (int mt = wsub; mt < vt; mt += wn) {
           uint32_t a[4];
           ldmatrix_x4_trans(vs_a + (uint32_t)((((m >> 1) * 8 + rr) * kStatLd + mt * 16 + (m & 1) * 8) * 2), a[0], a[1], a[2], a[3]);
           float acc[8][4];
@@ -410,9 +419,8 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
               if (acc[j][i] != 0.f) atomicAdd(&S_s[vi * 64 + hj], acc[j][i]);
             }
         }
-        // column sums: lane handles units lane and lane + 32
-#pragma unroll
-        for (int u = lane; u < 64; u += 32) {
+        // column sums: the group's lanes split the 64 units
+        for (int u = lane + 32 * wsub; u < 64; u += 32 * wn) {
           float cv = 0.f, chh = 0.f;
 #pragma unroll
           for (int row = 0; row < 16; ++row) {
@@ -481,7 +489,7 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   const bool full = (a.nV % 64 == 0) && (a.nH % 64 == 0) && vwords == hwords && (vwords == 1 || vwords == 2 || vwords == 4);
   // very few chains: split words in halves over twice the warps (one Philox group per warp)
   bool half = false;
-  if (full && !fuse && wn == vwords && n_groups * wn * 2 <= (int64_t)sm_count * 4) { half = true; wn *= 2; }
+  if (full && wn == vwords && n_groups * wn * 2 <= (int64_t)sm_count * 4) { half = true; wn *= 2; }
   int groups = 8 / wn;
   while (groups > 1 && ceil_div64(n_groups, groups) < sm_count) groups >>= 1;
   a.wn = wn; a.groups = groups;

@@ -24,6 +24,7 @@ int general_energy(const rbm_b200_params* p, const float* v, const float* h, flo
 int general_negative_phase(const float* v, const float* h, int64_t B, int nV, int nH, float scale,
                            float* S_vh, float* S_v, float* S_h, cudaStream_t st);
 int stats_zero(float* S_vh, float* S_v, float* S_h, int nV, int nH, cudaStream_t st);
+int stats_energy(const rbm_b200_params* p, const float* S_vh, const float* S_v, const float* S_h, float* E, cudaStream_t st);
 int stats_scale(float* S_vh, float* S_v, float* S_h, int nV, int nH, float scale, cudaStream_t st);
 
 // gibbs_smem.cu — persistent kernel, W (bf16) resident in shared memory

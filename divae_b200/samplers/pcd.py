@@ -95,12 +95,13 @@ class PCD(BaseSampler):
             S = torch.empty((nV, nH), dtype=torch.float32, device=dev)
             sv = torch.empty(nV, dtype=torch.float32, device=dev)
             sh = torch.empty(nH, dtype=torch.float32, device=dev)
+            e = torch.empty((), dtype=torch.float32, device=dev)
             with _ops._on_device(dev):
                 _lib.check(lib.rbm_b200_block_gibbs_stats(
                     ctypes.byref(p), _ops._ptr(v), _ops._ptr(h), B, k, 1 if init_chains else 0, self._seed,
                     self._chain_offset, step_offset, self._variant, _ops._ptr(ws), nbytes, float(stats_scale),
-                    _ops._ptr(S), _ops._ptr(sv), _ops._ptr(sh), _ops._stream()), "block_gibbs_stats")
-            return v, h, (S, sv, sh)
+                    _ops._ptr(S), _ops._ptr(sv), _ops._ptr(sh), _ops._ptr(e), _ops._stream()), "block_gibbs_stats")
+            return v, h, (S, sv, sh), e
         with _ops._on_device(dev):
             _lib.check(lib.rbm_b200_block_gibbs(
                 ctypes.byref(p), _ops._ptr(v), _ops._ptr(h), B, k, 1 if init_chains else 0, self._seed,
@@ -168,8 +169,9 @@ class PCD(BaseSampler):
         world = 1
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             world = torch.distributed.get_world_size(group)
-        v, h, (S, sv, sh) = self.block_gibbs_sampling(_stats_scale=1.0 / (self._batch_size * world))
+        v, h, (S, sv, sh), e = self.block_gibbs_sampling(_stats_scale=1.0 / (self._batch_size * world))
         if world > 1:
             from .. import dist as _dist
             S, sv, sh = _dist.allreduce_stats(S, sv, sh, group=group)
-        return _ops.energy_exp_from_stats(self._RBM, S, sv, sh), (S, sv, sh)
+            e = None    # the local value covers this shard only: recompute from the allreduced statistics
+        return _ops.energy_exp_from_stats(self._RBM, S, sv, sh, value=e), (S, sv, sh)

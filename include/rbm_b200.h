@@ -160,12 +160,14 @@ RBM_B200_API int rbm_b200_negative_phase(const float *v, const float *h, int64_t
  * divae.yaml and the *_deep variant) the statistics are computed INSIDE the final sweep of the
  * persistent shared-memory kernel from the on-chip states (v^T h by tensor-core MMA, raw counts
  * added atomically, scaled once); larger priors run the statistics kernels right after the chain.
+ * energy_exp (device scalar, may be NULL; needs the fp32 W): -(<W,S_vh> + a.S_v + c.S_h), i.e. the mean
+ * energy of the batch when scale = 1/B — the value GumBolt.energy_exp returns for these samples.
  * Replaces gumbolt.py:102-104 / dvaepp.py:141-159 (sampler call + energy_exp on its samples). */
 RBM_B200_API int rbm_b200_block_gibbs_stats(const rbm_b200_params *p, float *v, float *h, int64_t B,
                                             int32_t k, int init_chains, uint64_t seed, uint64_t chain_offset,
                                             uint64_t step_offset, int variant, void *workspace,
                                             size_t workspace_bytes, float scale, float *S_vh, float *S_v,
-                                            float *S_h, void *stream);
+                                            float *S_h, float *energy_exp, void *stream);
 
 /* One CD-k parameter update of a vanilla RBM, in place: Contrastive_Divergence.contrastive_divergence
  * (sandbox/rbm_standalone.py:66-121; the in-tree models/samplers/contrastiveDivergence.py does not parse).

@@ -93,7 +93,7 @@ def test_negative_phase_statistics_fused_into_the_final_sweep(nV, nH, B, k):
     W, a, c = rand_params(nV, nH, 0.3, nV + nH)
     rbm = make_rbm(W, a, c)
     s = divae_b200.PCD(batch_size=B, RBM=rbm, n_gibbs_sampling_steps=k, seed=23)
-    v, h, (S, sv, sh) = s.block_gibbs_sampling(_stats_scale=1.0)
+    v, h, (S, sv, sh), _e = s.block_gibbs_sampling(_stats_scale=1.0)
     vn, hn = v.cpu().numpy().astype(np.float64), h.cpu().numpy().astype(np.float64)
     assert (S.cpu().numpy() == vn.T @ hn).all()
     assert (sv.cpu().numpy() == vn.sum(0)).all() and (sh.cpu().numpy() == hn.sum(0)).all()
