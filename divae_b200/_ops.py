@@ -38,6 +38,16 @@ class ParamPack:
         self._packed = None
         self._packed_key = None
 
+    # the cache holds ctypes structs and device pointers: never pickled / deep-copied, rebuilt on first use
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+    def __deepcopy__(self, memo):
+        return ParamPack()
+
     def pack(self, rbm, need_bf16):
         Wp, ap, cp = rbm.weights, rbm.visible_bias, rbm.hidden_bias
         pkey = (id(Wp), Wp._version, id(ap), ap._version, id(cp), cp._version, Wp.data_ptr(), need_bf16)

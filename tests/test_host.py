@@ -151,3 +151,24 @@ def test_collectives_world_size_2_gloo():
 def test_logsumexp_single_process():
     x = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
     assert abs(bdist.logsumexp_allreduce(x).item() - torch.logsumexp(x, 0).item()) < 1e-12
+
+
+def test_modules_survive_pickle_and_deepcopy():
+    """torch.save(model) / copy.deepcopy(model) of reference-style models must keep working: the ctypes
+    parameter cache is transient state."""
+    import copy
+    import io
+    import pickle
+    r = divae_b200.RBM(8, 6)
+    s = divae_b200.PCD(batch_size=4, RBM=r, n_gibbs_sampling_steps=3, seed=5)
+    g = divae_b200.GibbsSampler(RBM=r, n_gibbs_sampling_steps=2)
+    r._pack._packed = object()           # pretend a call has populated the cache
+    r2, s2, g2 = copy.deepcopy(r), copy.deepcopy(s), copy.deepcopy(g)
+    assert torch.equal(r2.weights, r.weights) and s2._RBM is not s._RBM and s2._seed == 5
+    buf = io.BytesIO()
+    torch.save(s, buf)
+    buf.seek(0)
+    s3 = torch.load(buf, weights_only=False)
+    assert s3.get_batch_size() == 4 and torch.equal(s3._RBM.weights, r.weights)
+    assert pickle.loads(pickle.dumps(g)).n_gibbs_sampling_steps == 2
+    s3.load_state_dict(s.state_dict())
