@@ -17,35 +17,38 @@ namespace rbm {
 
 constexpr int GBM = 64, GBN = 64, GBK = 16;  // CTA tile: 64 rows x 64 units, 256 threads, 4x4 per thread
 
-// acc[i][j] = sum_k in[row0 + ty*4 + i][k] * Wop[k][n0 + tx*4 + j]
+// acc[i][j] = sum_k in[row0 + ty*T + i][k] * Wop[k][n0 + tx*T + j]      (CTA tile 16T x 16T, 256 threads)
 // TRANS = false: Wop[k][n] = W[k*ldw + n]   (v -> h, K = nV, N = nH)
 // TRANS = true : Wop[k][n] = W[n*ldw + k]   (h -> v, K = nH, N = nV)
-template <bool TRANS>
+// T = 4: 64x64 tiles (throughput); T = 2: 32x32 tiles for small problems, 4x the CTAs and a 4x shorter
+// K-serial loop per CTA (the CD-1 / PCD-batch regime is latency-bound, see profiles/r01_launches_cd1.csv).
+template <bool TRANS, int T>
 __device__ __forceinline__ void sgemm_tile(const float* __restrict__ in, const float* __restrict__ W,
                                            int64_t B, int K, int N, int ldw, int64_t row0, int n0,
-                                           float (&acc)[4][4]) {
-  __shared__ float As[GBK][GBM + 4];
-  __shared__ float Bs[GBK][GBN + 4];
+                                           float (&acc)[T][T]) {
+  constexpr int BT = 16 * T;
+  __shared__ float As[GBK][BT + 4];
+  __shared__ float Bs[GBK][BT + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < T; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < T; ++j) acc[i][j] = 0.f;
 
   // global -> registers for one K block (the NEXT block is fetched while the current one is multiplied,
   // so the global-load latency is off the critical path of this K-serial loop)
-  float ra[4], rb[4];
+  float ra[T], rb[T];
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
+    for (int l = 0; l < T; ++l) {
       const int idx = tid + l * 256;
       const int r = idx >> 4, kk = idx & 15;
       const int64_t row = row0 + r;
       const int k = k0 + kk;
       ra[l] = (row < B && k < K) ? in[row * (int64_t)K + k] : 0.f;
       if (!TRANS) {
-        const int kb = idx >> 6, n = idx & 63;
+        const int kb = idx / BT, n = idx % BT;
         const int kx = k0 + kb, col = n0 + n;
         rb[l] = (kx < K && col < N) ? W[(int64_t)kx * ldw + col] : 0.f;
       } else {
@@ -58,49 +61,50 @@ __device__ __forceinline__ void sgemm_tile(const float* __restrict__ in, const f
   fetch(0);
   for (int k0 = 0; k0 < K; k0 += GBK) {
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
+    for (int l = 0; l < T; ++l) {
       const int idx = tid + l * 256;
       As[idx & 15][idx >> 4] = ra[l];
-      if (!TRANS) Bs[idx >> 6][idx & 63] = rb[l];
+      if (!TRANS) Bs[idx / BT][idx % BT] = rb[l];
       else Bs[idx & 15][idx >> 4] = rb[l];
     }
     __syncthreads();
     if (k0 + GBK < K) fetch(k0 + GBK);
 #pragma unroll
     for (int kk = 0; kk < GBK; ++kk) {
-      float a[4], b[4];
+      float a[T], b[T];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < T; ++i) a[i] = As[kk][ty * T + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < T; ++j) b[j] = Bs[kk][tx * T + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < T; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < T; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 }
 
-template <bool TRANS, int MODE>
+template <bool TRANS, int MODE, int T>
 __global__ void __launch_bounds__(256)
 half_step_kernel(const float* __restrict__ in, const float* __restrict__ W,
                  const float* __restrict__ bias, float* __restrict__ out,
                  const float* __restrict__ U, int64_t B, int K, int N, int ldw,
                  DrawCtx ctx, uint64_t chain_offset, int64_t u_row_stride, float* __restrict__ probs_out) {
-  const int64_t row0 = (int64_t)blockIdx.x * GBM;
-  const int n0 = blockIdx.y * GBN;
-  float acc[4][4];
-  sgemm_tile<TRANS>(in, W, B, K, N, ldw, row0, n0, acc);
+  constexpr int BT = 16 * T;
+  const int64_t row0 = (int64_t)blockIdx.x * BT;
+  const int n0 = blockIdx.y * BT;
+  float acc[T][T];
+  sgemm_tile<TRANS, T>(in, W, B, K, N, ldw, row0, n0, acc);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t row = row0 + ty * 4 + i;
+  for (int i = 0; i < T; ++i) {
+    const int64_t row = row0 + ty * T + i;
     if (row >= B) continue;
     const uint32_t chain = (uint32_t)(chain_offset + (uint64_t)row);
 #pragma unroll
-    for (int jp = 0; jp < 2; ++jp) {  // column pairs share one Philox block
-      const int col = n0 + tx * 4 + jp * 2;
+    for (int jp = 0; jp < T / 2; ++jp) {  // column pairs share one Philox block
+      const int col = n0 + tx * T + jp * 2;
       if (col >= N) continue;
       uint4 w = make_uint4(0, 0, 0, 0);
       if (MODE == RBM_B200_MODE_SAMPLE) w = draw_block(ctx, unit_block_of(col), chain);
@@ -153,7 +157,7 @@ energy_partial_kernel(const float* __restrict__ v, const float* __restrict__ h,
   const int64_t row0 = (int64_t)blockIdx.x * GBM;
   const int n0 = blockIdx.y * GBN;
   float acc[4][4];
-  sgemm_tile<false>(v, W, B, nV, nH, nH, row0, n0, acc);
+  sgemm_tile<false, 4>(v, W, B, nV, nH, nH, row0, n0, acc);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -264,11 +268,22 @@ static int launch_half_step(const rbm_b200_params* p, int direction, const float
   const int K = direction == 0 ? p->n_visible : p->n_hidden;
   const int N = direction == 0 ? p->n_hidden : p->n_visible;
   const float* bias = direction == 0 ? p->hbias : p->vbias;
-  dim3 grid((unsigned)ceil_div64(B, GBM), (unsigned)ceil_div(N, GBN));
-  if (direction == 0)
-    half_step_kernel<false, MODE><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset, broadcast_u ? 0 : (int64_t)N, probs_out);
-  else
-    half_step_kernel<true, MODE><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset, broadcast_u ? 0 : (int64_t)N, probs_out);
+  // small problems are latency-bound: 32x32 tiles give 4x the CTAs and a 4x shorter K loop per CTA
+  const bool small = ceil_div64(B, GBM) * ceil_div(N, GBN) < 74;
+  const int64_t urs = broadcast_u ? 0 : (int64_t)N;
+  if (small) {
+    dim3 grid((unsigned)ceil_div64(B, 32), (unsigned)ceil_div(N, 32));
+    if (direction == 0)
+      half_step_kernel<false, MODE, 2><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset, urs, probs_out);
+    else
+      half_step_kernel<true, MODE, 2><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset, urs, probs_out);
+  } else {
+    dim3 grid((unsigned)ceil_div64(B, GBM), (unsigned)ceil_div(N, GBN));
+    if (direction == 0)
+      half_step_kernel<false, MODE, 4><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset, urs, probs_out);
+    else
+      half_step_kernel<true, MODE, 4><<<grid, 256, 0, st>>>(in, p->W, bias, out, U, B, K, N, p->n_hidden, ctx, chain_offset, urs, probs_out);
+  }
   return check_launch("half_step_kernel");
 }
 
