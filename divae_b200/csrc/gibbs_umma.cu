@@ -302,11 +302,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
       const int col0 = n_blk * BLOCK_N + col_in_tile;
       const bool live = col0 < ep.ldo;   // tile overhang beyond the padded unit count
       const uint32_t blk0 = (uint32_t)(col0 >> 5) * 4u;
+#ifndef RBM_DEBUG_NO_WAIT_READ
       if (live) {
         // the previous TMA store of this warp must have finished READING the staging box
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
       }
+#endif
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t r[16];
