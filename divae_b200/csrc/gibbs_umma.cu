@@ -93,6 +93,17 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// one lane of a converged warp (the warp stays convergent, so descriptors can live in uniform registers)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- cluster-pair (cta_group::2) flavours
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -487,7 +498,11 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
   } else if (warp_idx == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0 && is_leader) {
+    // The WHOLE warp runs the loop (waits, descriptor arithmetic) so everything stays warp-uniform and in
+    // uniform registers; one elected lane issues the tcgen05 instructions.  (With a single-lane loop the
+    // compiler emitted ~110 dependent instructions per K block - vector->uniform register moves in ELECT
+    // loops - and the tensor pipe idled a third of the time waiting for its issuer: profiles/r01_mma_issue.txt.)
+    if (is_leader) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M * CTAS, BLOCK_N, B_MN_MAJOR);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
@@ -501,20 +516,26 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * L::kStageBytes;
           const uint32_t sb = sa + kABytes;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t bdesc = B_MN_MAJOR ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                              : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            if (CTAS == 2) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+              const uint64_t bdesc = B_MN_MAJOR ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                                : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+              if (CTAS == 2) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+            if (CTAS == 2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
           }
-          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
-          if (CTAS == 2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if (CTAS == 2) umma_commit_pair(tmem_full_bar(as)); else umma_commit(tmem_full_bar(as));
+        if (elect_one_sync()) {
+          if (CTAS == 2) umma_commit_pair(tmem_full_bar(as)); else umma_commit(tmem_full_bar(as));
+        }
+        __syncwarp();
       }
     }
   } else if (warp_idx >= 4) {
@@ -666,25 +687,30 @@ umma_multistep_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_co
           }
         }
       } else if (warp_idx == 1) {
-        if (lane == 0) {
-          // ---- MMA issuer (the accumulator is free: the previous half-step ended with a cluster barrier)
+        {
+          // ---- MMA issuer (the accumulator is free: the previous half-step ended with a cluster barrier).
+          // Whole warp, warp-uniform; one elected lane issues (see umma_half_step_kernel).
           const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, dir == 0);
           for (int kb = 0; kb < args.k_blocks[dir]; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tcgen05_fence_after();
             const uint32_t sa = smem_base + stage * L::kStageBytes;
             const uint32_t sb = sa + kABytes;
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-              const uint64_t bdesc = dir == 0 ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                              : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-              umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                const uint64_t adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+                const uint64_t bdesc = dir == 0 ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                                : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+                umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(empty_bar(stage));
             }
-            umma_commit(empty_bar(stage));
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(tmem_full_bar);
+          if (elect_one_sync()) umma_commit(tmem_full_bar);
+          __syncwarp();
         }
       } else if (warp_idx >= 4) {
         // ---- epilogue
