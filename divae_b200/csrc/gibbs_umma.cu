@@ -456,7 +456,8 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   if (warp_idx == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0 && args.debug_mode != 2) {
+    // (whole warp, warp-uniform; one elected lane issues the copies - same reasoning as the MMA issuer)
+    if (args.debug_mode != 2) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const int n_blk = tile % args.n_tiles, m_blk = tile / args.n_tiles;
@@ -466,32 +467,35 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * L::kStageBytes;
           const uint32_t sb = sa + kABytes;
-          if (CTAS == 1) {
-            mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
-            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, row0);
-            if (B_MN_MAJOR) {
-              // W[k rows][n cols]: one [64 x 64] box per 64-column MN block, 8 KB apart (LBO)
+          if (elect_one_sync()) {
+            if (CTAS == 1) {
+              mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
+              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, row0);
+              if (B_MN_MAJOR) {
+                // W[k rows][n cols]: one [64 x 64] box per 64-column MN block, 8 KB apart (LBO)
 #pragma unroll
-              for (int nb = 0; nb < kBCols / 64; ++nb)
-                tma_load_2d(sb + nb * (BLOCK_K * 128), &tmap_b, full_bar(stage), ncol0 + nb * 64, kb * BLOCK_K);
+                for (int nb = 0; nb < kBCols / 64; ++nb)
+                  tma_load_2d(sb + nb * (BLOCK_K * 128), &tmap_b, full_bar(stage), ncol0 + nb * 64, kb * BLOCK_K);
+              } else {
+                // W[n rows][k cols]: one [kBCols x 64] box, rows of 128 B
+                tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BLOCK_K, ncol0);
+              }
             } else {
-              // W[n rows][k cols]: one [kBCols x 64] box, rows of 128 B
-              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BLOCK_K, ncol0);
-            }
-          } else {
-            // both CTAs credit the LEADER's full barrier (2 arrivals + the bytes of both CTAs)
-            const uint32_t lead_full = mapa_u32(full_bar(stage), 0);
-            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * L::kStageBytes);
-            else mbar_arrive_cluster(lead_full);
-            tma_load_2d_pair(sa, &tmap_a, lead_full, kb * BLOCK_K, row0);
-            if (B_MN_MAJOR) {
+              // both CTAs credit the LEADER's full barrier (2 arrivals + the bytes of both CTAs)
+              const uint32_t lead_full = mapa_u32(full_bar(stage), 0);
+              if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * L::kStageBytes);
+              else mbar_arrive_cluster(lead_full);
+              tma_load_2d_pair(sa, &tmap_a, lead_full, kb * BLOCK_K, row0);
+              if (B_MN_MAJOR) {
 #pragma unroll
-              for (int nb = 0; nb < kBCols / 64; ++nb)
-                tma_load_2d_pair(sb + nb * (BLOCK_K * 128), &tmap_b, lead_full, ncol0 + nb * 64, kb * BLOCK_K);
-            } else {
-              tma_load_2d_pair(sb, &tmap_b, lead_full, kb * BLOCK_K, ncol0);
+                for (int nb = 0; nb < kBCols / 64; ++nb)
+                  tma_load_2d_pair(sb + nb * (BLOCK_K * 128), &tmap_b, lead_full, ncol0 + nb * 64, kb * BLOCK_K);
+              } else {
+                tma_load_2d_pair(sb, &tmap_b, lead_full, kb * BLOCK_K, ncol0);
+              }
             }
           }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -668,21 +672,24 @@ umma_multistep_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_co
       const CUtensorMap* tm_a = dir ? &tm_a1 : &tm_a0;
       const CUtensorMap* tm_b = dir ? &tm_b1 : &tm_b0;
       if (warp_idx == 0) {
-        if (lane == 0) {
+        {
           // ---- TMA producer: this row block's state (A) and tile n_blk of W (B: MN-major for dir 0, K-major for dir 1)
           for (int kb = 0; kb < args.k_blocks[dir]; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * L::kStageBytes;
             const uint32_t sb = sa + kABytes;
-            mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
-            tma_load_2d(sa, tm_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
-            if (dir == 0) {
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
+              tma_load_2d(sa, tm_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+              if (dir == 0) {
 #pragma unroll
-              for (int nb = 0; nb < BLOCK_N / 64; ++nb)
-                tma_load_2d(sb + nb * (BLOCK_K * 128), tm_b, full_bar(stage), n_blk * BLOCK_N + nb * 64, kb * BLOCK_K);
-            } else {
-              tma_load_2d(sb, tm_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+                for (int nb = 0; nb < BLOCK_N / 64; ++nb)
+                  tma_load_2d(sb + nb * (BLOCK_K * 128), tm_b, full_bar(stage), n_blk * BLOCK_N + nb * 64, kb * BLOCK_K);
+              } else {
+                tma_load_2d(sb, tm_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+              }
             }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
