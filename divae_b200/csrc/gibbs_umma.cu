@@ -1058,6 +1058,7 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   if ((rc = make_tmap(&tm_w_k_pair, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 128))) return rc;
 
   // Few chains: one launch for all 2k half-steps (cluster per 128-chain row block, see umma_multistep_kernel)
+  bool ran_multistep = false;
   {
     const int nt_h = ceil_div(pl.nHp, pl.bn_h), nt_v = ceil_div(pl.nVp, pl.bn_v);
     const int cs = std::max(nt_h, nt_v);
@@ -1081,12 +1082,11 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
       rc = pl.bn_h == 256 ? launch_multistep<256, EPI_GIBBS, EPI_GIBBS>(tm, ma, m_tiles, cs, st)
                           : launch_multistep<128, EPI_GIBBS, EPI_GIBBS>(tm, ma, m_tiles, cs, st);
       if (rc) return rc;
-      chunk_rows = pl.rows_pad;
-      goto convert_out;
+      ran_multistep = true;
     }
   }
 
-  for (int64_t r0 = 0; r0 < pl.rows_pad; r0 += chunk_rows) {
+  for (int64_t r0 = 0; !ran_multistep && r0 < pl.rows_pad; r0 += chunk_rows) {
     const int64_t rows = std::min(chunk_rows, pl.rows_pad - r0);
     __nv_bfloat16* Vc = Vs + r0 * pl.nVp;
     __nv_bfloat16* Hc = Hs + r0 * pl.nHp;
@@ -1118,7 +1118,6 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
       if (rc) return rc;
     }
   }
-convert_out:
   // back to the reference's dtype
   {
     const int64_t nv = B * pl.nV, nh = B * pl.nH;
