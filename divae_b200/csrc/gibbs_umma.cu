@@ -207,6 +207,8 @@ struct SmemLayout {
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers/tmem ptr + alignment slack
 };
 
+constexpr uint32_t kKfMagic = 0x4B000000u;   // float 2^23: OR-ing a 16-bit field into its mantissa gives 2^23 + k exactly
+
 struct HalfStepArgs {
   __nv_bfloat16* out;      // [rows, ldo] destination state (bf16 {0,1}); written through tmap_out, kept for reference
   const float* nbias;      // [>= n_tiles*BLOCK_N]  -bias * log2(e), zero padded
@@ -223,6 +225,7 @@ struct HalfStepArgs {
   float* wpart;            // [rows_pad, wpart_ld] running log-weight partials (log2 units)
   int wpart_ld;
   int debug_mode;          // profiling only (env RBM_B200_DEBUG_MODE): 1 = skip epilogue math, 2 = skip TMA+MMA
+  uint32_t kf_magic;       // kKfMagic, passed at run time (see EpiParams)
 };
 
 // Epilogue flavours
@@ -272,6 +275,9 @@ struct EpiParams {
   DrawCtx ctx;
   float scale, bmul, ratio;   // annealed flavours (see HalfStepArgs)
   int debug_mode;
+  // 0x4B000000 (float 2^23) handed over as a RUN-TIME value: as a literal, ptxas encodes it as PRMT's
+  // immediate and then has to materialise the byte selector in a register before every PRMT
+  uint32_t kf_magic;
 };
 
 // Epilogue of ONE 128 x BLOCK_N tile for one warp: TMEM -> decisions -> swizzled smem box -> TMA store.
@@ -346,7 +352,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
             const int slot = 2 * (cc >> 3) + (cc & 1);
             const uint32_t word = w[b][slot >> 1];
             // float(8388608 + k16) with one byte-permute, minus 2^23 -> exact float(k16)
-            const uint32_t mbits = (slot & 1) ? __byte_perm(word, 0x4B000000u, 0x7632) : __byte_perm(word, 0x4B000000u, 0x7610);
+            const uint32_t mbits = (slot & 1) ? __byte_perm(word, ep.kf_magic, 0x7632) : __byte_perm(word, ep.kf_magic, 0x7610);
             const float kf = __uint_as_float(mbits) - 8388608.0f;
             const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbv[i4])
                                                : fmaf(__uint_as_float(r[c16]), ep.scale, nbv[i4] * ep.bmul);
@@ -359,10 +365,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
               if (col0 + cc < ep.n_valid)
                 wsum += (akm1 - ak) + lg2_approx(fminf(q.s, 1.2089258e24f)) - lg2_approx(1.0f + ex2_approx(akm1));
             }
-            const bool one = q.d >= q.s;
+            // fp32 1.0 / 0.0 straight from the compare (FSET); the top halves of two of them are the bf16 pair
+            const uint32_t onef = __float_as_uint(q.d >= q.s ? 1.0f : 0.0f);
             amb = amb || (__float_as_uint(q.d) < __float_as_uint(q.s));
-            const uint32_t val = (c16 & 1) ? 0x3F800000u : 0x3F80u;   // bf16 1.0 in the high / low half
-            if (c16 & 1) pk[c16 >> 1] |= one ? val : 0u; else pk[c16 >> 1] = one ? val : 0u;
+            if (c16 & 1) pk[c16 >> 1] = __byte_perm(pk[c16 >> 1], onef, 0x7632); else pk[c16 >> 1] = onef;
           }
         }
         if (amb) {
@@ -558,6 +564,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       EpiParams ep;
       ep.nbias = args.nbias; ep.ldo = args.ldo; ep.n_valid = args.n_valid; ep.ctx = args.ctx;
       ep.scale = args.scale; ep.bmul = args.bmul; ep.ratio = args.ratio; ep.debug_mode = args.debug_mode;
+      ep.kf_magic = args.kf_magic;
       epilogue_tile<BLOCK_N, EPI>(
           ep, &tmap_out, tmem_base + (uint32_t)(as * BLOCK_N), n_blk, row_base, chain, quarter, cq, lane, stage_warp, wsum,
           [&] { mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u); },
@@ -606,6 +613,7 @@ struct MultiArgs {
   const float* betas;      // annealed flavours: beta index of half-step t is 1 + t/2
   float* wpart;            // AIS: [rows, wpart_ld] log-weight partials (log2 units), added to at the end
   int wpart_ld;
+  uint32_t kf_magic;       // kKfMagic (see EpiParams)
 };
 
 template <int BLOCK_N, int EPI0, int EPI1>
@@ -725,6 +733,7 @@ umma_multistep_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_co
         ep.nbias = args.nbias[dir]; ep.ldo = args.ldo[dir]; ep.n_valid = args.n_valid[dir];
         ep.ctx = make_draw_ctx(args.seed, args.step_offset + (uint64_t)t, args.tag);
         ep.scale = -1.4426950408889634f; ep.bmul = 1.f; ep.ratio = 0.f; ep.debug_mode = 0;
+        ep.kf_magic = args.kf_magic;
         if (EPI0 != EPI_GIBBS) {
           const float bk = __ldg(args.betas + 1 + (t >> 1)), bkm1 = __ldg(args.betas + (t >> 1));
           ep.scale = -1.4426950408889634f * bk;
@@ -933,6 +942,7 @@ int launch_half_step_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   static const int debug_mode = [] { const char* e = getenv("RBM_B200_DEBUG_MODE"); return e ? atoi(e) : 0; }();
   HalfStepArgs a2 = a;
   a2.debug_mode = debug_mode;
+  a2.kf_magic = kKfMagic;
   const int tiles = (a.m_tiles / CTAS) * a.n_tiles;
   const int grid = CTAS * std::min(tiles, sm_count / CTAS);
   cudaLaunchConfig_t cfg{};
@@ -1078,7 +1088,7 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
       ma.n_valid[0] = pl.nH; ma.n_valid[1] = pl.nV; ma.n_tiles[0] = nt_h; ma.n_tiles[1] = nt_v;
       ma.k_blocks[0] = pl.nVp / BLOCK_K; ma.k_blocks[1] = pl.nHp / BLOCK_K;
       ma.steps = 2 * k; ma.first_dir = 0; ma.seed = seed; ma.chain_offset = chain_offset; ma.step_offset = step_offset;
-      ma.tag = TAG_GIBBS;
+      ma.tag = TAG_GIBBS; ma.kf_magic = kKfMagic;
       rc = pl.bn_h == 256 ? launch_multistep<256, EPI_GIBBS, EPI_GIBBS>(tm, ma, m_tiles, cs, st)
                           : launch_multistep<128, EPI_GIBBS, EPI_GIBBS>(tm, ma, m_tiles, cs, st);
       if (rc) return rc;
@@ -1213,7 +1223,7 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
       ma.k_blocks[0] = pl.nVp / BLOCK_K; ma.k_blocks[1] = pl.nHp / BLOCK_K;
       ma.steps = 2 * K - 1;            // K hidden steps, K-1 visible steps (the last transition is skipped)
       ma.first_dir = 0; ma.seed = seed; ma.chain_offset = chain_offset; ma.step_offset = 2;   // half-step counter 2k / 2k+1
-      ma.tag = TAG_AIS; ma.betas = betas_dev; ma.wpart = wpart; ma.wpart_ld = pl.wpart_ld;
+      ma.tag = TAG_AIS; ma.kf_magic = kKfMagic; ma.betas = betas_dev; ma.wpart = wpart; ma.wpart_ld = pl.wpart_ld;
       rc = pl.bn_h == 256 ? launch_multistep<256, EPI_AIS_WEIGHT, EPI_ANNEALED>(tm, ma, m_tiles, cs, st)
                           : launch_multistep<128, EPI_AIS_WEIGHT, EPI_ANNEALED>(tm, ma, m_tiles, cs, st);
       if (rc) return rc;
