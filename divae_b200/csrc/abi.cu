@@ -175,8 +175,10 @@ static int block_gibbs_impl(const rbm_b200_params* p, float* v, float* h, int64_
   }
   if (chosen == RBM_B200_VARIANT_UMMA) {
     RBM_REQUIRE(p->W_bf16, RBM_B200_ERR_INVALID, "UMMA variant needs W_bf16");
+    const bool fuse = S_vh != nullptr && k > 0;
+    if (stats_fused) *stats_fused = fuse;
     return umma_block_gibbs(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, workspace,
-                            workspace_bytes, st);
+                            workspace_bytes, st, fuse ? S_vh : nullptr, fuse ? S_v : nullptr, fuse ? S_h : nullptr);
   }
   RBM_REQUIRE(p->W, RBM_B200_ERR_INVALID, "GENERAL variant needs fp32 W");
   if (init_chains) {

@@ -325,17 +325,38 @@ int general_energy(const rbm_b200_params* p, const float* v, const float* h, flo
 }
 
 // E = -(<W, S_vh> + a.S_v + c.S_h): the mean energy of the batch whose (scaled) statistics are S_*.
-// One CTA, fixed-order reduction: deterministic.
+// One cluster of eight CTAs: every CTA reduces a fixed, interleaved share of <W, S_vh> in a fixed order,
+// rank 0 adds the eight partial sums (read over distributed shared memory) in rank order - deterministic,
+// no scratch buffer, and eight SMs' worth of load bandwidth instead of one (165 -> ~15 us at 1024 x 1024).
+constexpr int kEnergyCluster = 8;
+
 __global__ void __launch_bounds__(1024)
 stats_energy_kernel(const float* __restrict__ W, const float* __restrict__ a, const float* __restrict__ c,
                     const float* __restrict__ S, const float* __restrict__ sv, const float* __restrict__ sh,
                     int nV, int nH, float* __restrict__ E) {
   __shared__ float red[32];
-  float s = 0.f;
+  __shared__ float cta_sum;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const int64_t n = (int64_t)nV * nH;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(W[i], S[i], s);
-  for (int i = threadIdx.x; i < nV; i += blockDim.x) s = fmaf(a[i], sv[i], s);
-  for (int i = threadIdx.x; i < nH; i += blockDim.x) s = fmaf(c[i], sh[i], s);
+  const bool vec = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(S)) & 15) == 0;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (vec) {
+    const float4* W4 = reinterpret_cast<const float4*>(W);
+    const float4* S4 = reinterpret_cast<const float4*>(S);
+    for (int64_t i = (int64_t)rank * blockDim.x + threadIdx.x; i < (n >> 2); i += (int64_t)kEnergyCluster * blockDim.x) {
+      const float4 w = __ldg(W4 + i), x = __ldg(S4 + i);
+      s0 = fmaf(w.x, x.x, s0); s1 = fmaf(w.y, x.y, s1); s2 = fmaf(w.z, x.z, s2); s3 = fmaf(w.w, x.w, s3);
+    }
+  } else {
+    for (int64_t i = (int64_t)rank * blockDim.x + threadIdx.x; i < n; i += (int64_t)kEnergyCluster * blockDim.x)
+      s0 = fmaf(W[i], S[i], s0);
+  }
+  float s = (s0 + s1) + (s2 + s3);
+  if (rank == 0) {
+    for (int i = threadIdx.x; i < nV; i += blockDim.x) s = fmaf(a[i], sv[i], s);
+    for (int i = threadIdx.x; i < nH; i += blockDim.x) s = fmaf(c[i], sh[i], s);
+  }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -344,12 +365,40 @@ stats_energy_kernel(const float* __restrict__ W, const float* __restrict__ a, co
     s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (threadIdx.x == 0) *E = -s;
+    if (threadIdx.x == 0) cta_sum = s;
   }
+  // partial sums visible cluster-wide
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (rank == 0 && threadIdx.x == 0) {
+    float total = 0.f;
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(&cta_sum);
+    for (uint32_t r = 0; r < (uint32_t)kEnergyCluster; ++r) {
+      uint32_t remote;
+      float part;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(part) : "r"(remote) : "memory");
+      total += part;
+    }
+    *E = -total;
+  }
+  // no CTA may exit while rank 0 still reads its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 int stats_energy(const rbm_b200_params* p, const float* S_vh, const float* S_v, const float* S_h, float* E, cudaStream_t st) {
-  stats_energy_kernel<<<1, 1024, 0, st>>>(p->W, p->vbias, p->hbias, S_vh, S_v, S_h, p->n_visible, p->n_hidden, E);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kEnergyCluster);
+  cfg.blockDim = dim3(1024);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kEnergyCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RBM_CUDA_TRY(cudaLaunchKernelEx(&cfg, stats_energy_kernel, (const float*)p->W, (const float*)p->vbias,
+                                  (const float*)p->hbias, S_vh, S_v, S_h, (int)p->n_visible, (int)p->n_hidden, E));
   return check_launch("stats_energy_kernel");
 }
 

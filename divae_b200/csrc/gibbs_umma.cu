@@ -181,12 +181,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-// 32-bit instruction descriptor: D fp32, A/B bf16, M x N, A K-major, B major selectable.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major) {
+// 32-bit instruction descriptor: D fp32, A/B bf16, M x N, A and B major selectable (0 = K-major).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major, bool a_mn_major = false) {
   return (1u << 4)                       // c_format = F32
          | (1u << 7)                     // a_format = BF16
          | (1u << 10)                    // b_format = BF16
-         | (0u << 15)                    // a_major  = K
+         | ((a_mn_major ? 1u : 0u) << 15)  // a_major
          | ((b_mn_major ? 1u : 0u) << 16)  // b_major
          | ((uint32_t)(N >> 3) << 17)    // n_dim
          | ((uint32_t)(M >> 4) << 24);   // m_dim
@@ -786,6 +786,20 @@ __global__ void bf16_to_f32_crop(const __nv_bfloat16* __restrict__ src, float* _
   const int c = (int)(idx % n);
   dst[idx] = __bfloat162float(src[r * ld + c]);
 }
+// same, eight units per thread (n % 8 == 0): one 16-byte load, two 16-byte stores
+__global__ void bf16_to_f32_crop8(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t B, int n, int ld) {
+  const int n8 = n >> 3;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * n8) return;
+  const int64_t r = idx / n8;
+  const int c = (int)(idx % n8) * 8;
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + r * ld + c));
+  float4* d = reinterpret_cast<float4*>(dst + r * n + c);
+  d[0] = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xFFFF0000u),
+                     __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xFFFF0000u));
+  d[1] = make_float4(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xFFFF0000u),
+                     __uint_as_float(q.w << 16), __uint_as_float(q.w & 0xFFFF0000u));
+}
 __global__ void pad_w_kernel(const uint16_t* __restrict__ W, uint16_t* __restrict__ Wp, int nV, int nH, int nVp, int nHp) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)nVp * nHp) return;
@@ -799,18 +813,31 @@ __global__ void nbias_kernel(const float* __restrict__ bias, float* __restrict__
 // Bernoulli(1/2) initial state straight into the bf16 state buffer (contract: 1 - (u16 >> 15), TAG_INIT)
 __global__ void init_chains_bf16_kernel(__nv_bfloat16* __restrict__ v, int64_t rows, int nV, int ld, DrawCtx ctx,
                                         uint64_t chain_offset) {
-  const int nblk = ld / 8;
+  // one 32-unit group (four Philox blocks, philox.cuh slot mapping) per thread: 64 contiguous bytes of the row
+  const int ngrp = ld / 32;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * nblk) return;
-  const int64_t row = idx / nblk;
-  const int blk = (int)(idx % nblk);
-  const uint4 w = draw_block(ctx, (uint32_t)blk, (uint32_t)(chain_offset + (uint64_t)row));
-  const int base = (blk >> 2) * 32 + (blk & 3) * 2;
+  if (idx >= rows * ngrp) return;
+  const int64_t row = idx / ngrp;
+  const int grp = (int)(idx % ngrp);
+  const uint32_t chain = (uint32_t)(chain_offset + (uint64_t)row);
+  uint32_t w[4][4];
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const int c = base + (s >> 1) * 8 + (s & 1);
-    if (c < ld) v[row * (int64_t)ld + c] = __float2bfloat16((c < nV && !(field16(w, s) >> 15)) ? 1.f : 0.f);
+  for (int b = 0; b < 4; ++b) {
+    const uint4 x = draw_block(ctx, (uint32_t)(grp * 4 + b), chain);
+    w[b][0] = x.x; w[b][1] = x.y; w[b][2] = x.z; w[b][3] = x.w;
   }
+  uint32_t pk[16];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const int b = (c & 7) >> 1, slot = 2 * (c >> 3) + (c & 1);
+    const uint32_t word = w[b][slot >> 1];
+    const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
+    const uint32_t one = (grp * 32 + c < nV && !(k16 >> 15)) ? 0x3F80u : 0u;   // v0 = 1 - (u16 >> 15)
+    if (c & 1) pk[c >> 1] |= one << 16; else pk[c >> 1] = one;
+  }
+  uint4* dst = reinterpret_cast<uint4*>(v + row * (int64_t)ld + grp * 32);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
 
 // AIS initial state v ~ p_A = Bernoulli(sigmoid(a)) (base-rate model with a_A = a), TAG_AIS_INIT
@@ -840,6 +867,183 @@ __global__ void ais_reduce_kernel(const float* __restrict__ wpart, int ld, int64
   double s = 0.0;
   for (int i = 0; i < ld; ++i) s += (double)wpart[b * ld + i];
   logw[b] = s * 0.6931471805599453;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Negative-phase statistics on the tensor cores:  S_vh += V^T H  over the chains of one K split
+// (the W-gradient of GumBolt.energy_exp at the sampler's states, models/autoencoders/gumbolt.py:109-134,
+// dvaepp.py:141-159).
+//   D[i, j] = sum_b V[b, i] * H[b, j]      M = visible units, N = hidden units, K = chains
+// Both operands are read straight from the bf16 state tiles [chains, units] the sampler leaves in the
+// workspace: a [64 chains x 64 units] TMA box IS one MN-major SWIZZLE_128B block, for A (V^T) and for B (H)
+// alike, so there is no transpose pass.  The tensor maps are built with B rows: chains of the padding
+// are zero-filled by TMA.  Counts are exact in fp32 (B <= 2^24 chains); the split-K partial tiles are added
+// to the zeroed S_vh with red.global.add.f32, and integer-valued sums do not depend on the order.
+constexpr int kStatsThreads = 256;   // warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+constexpr int kStatsStages = 4;
+
+struct StatsArgs {
+  float* S_vh;         // [nV, nH] fp32, raw counts are ADDED
+  int nV, nH;
+  int tiles_n;         // N tiles; blockIdx.x = split * tiles + m_blk * tiles_n + n_blk
+  int tiles;           // M tiles * N tiles
+  int k_blocks;        // ceil(B / 64)
+  int kb_per_split;
+};
+
+template <int BLOCK_N>
+constexpr int stats_smem_bytes() { return kStatsStages * (kABytes + BLOCK_N * BLOCK_K * 2) + 256 + 1024; }
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kStatsThreads, 1)
+umma_stats_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_h,
+                  const StatsArgs args) {
+  constexpr int kStageBytes = kABytes + BLOCK_N * BLOCK_K * 2;
+  constexpr int kBoxBytes = BLOCK_K * 128;   // one [64 chains x 64 units] box
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + kStatsStages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStatsStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStatsStages);
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kStatsStages * kStageBytes + 8 * (2 * kStatsStages + 1));
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = (int)blockIdx.x % args.tiles, split = (int)blockIdx.x / args.tiles;
+  const int m_blk = tile / args.tiles_n, n_blk = tile % args.tiles_n;
+  const int kb0 = split * args.kb_per_split;
+  const int nkb = min(args.k_blocks, kb0 + args.kb_per_split) - kb0;   // >= 1 (host)
+
+  if (warp_idx == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_v) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_h) : "memory");
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < kStatsStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp_idx == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"((uint32_t)BLOCK_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // TMA producer (warp-uniform loop, one elected lane issues)
+    int stage = 0; uint32_t phase = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t sa = smem_base + stage * kStageBytes;
+      const uint32_t sb = sa + kABytes;
+      const int chain0 = (kb0 + i) * BLOCK_K;
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+#pragma unroll
+        for (int mb = 0; mb < BLOCK_M / 64; ++mb)
+          tma_load_2d(sa + mb * kBoxBytes, &tmap_v, full_bar(stage), m_blk * BLOCK_M + mb * 64, chain0);
+#pragma unroll
+        for (int nb = 0; nb < BLOCK_N / 64; ++nb)
+          tma_load_2d(sb + nb * kBoxBytes, &tmap_h, full_bar(stage), n_blk * BLOCK_N + nb * 64, chain0);
+      }
+      __syncwarp();
+      if (++stage == kStatsStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp_idx == 1) {
+    // MMA issuer: A and B both MN-major (64-unit blocks LBO = 8 KB apart, 8-chain groups SBO = 1 KB apart)
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, true, true);
+    int stage = 0; uint32_t phase = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(full_bar(stage), phase);
+      tcgen05_fence_after();
+      const uint32_t sa = smem_base + stage * kStageBytes;
+      const uint32_t sb = sa + kABytes;
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t adesc = make_smem_desc(sa + k * (UMMA_K * 128), kBoxBytes, 1024);
+          const uint64_t bdesc = make_smem_desc(sb + k * (UMMA_K * 128), kBoxBytes, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+      }
+      __syncwarp();
+      if (++stage == kStatsStages) { stage = 0; phase ^= 1u; }
+    }
+    if (elect_one_sync()) umma_commit(tmem_full_bar);
+    __syncwarp();
+  } else if (warp_idx >= 4) {
+    // epilogue: lane = visible unit (TMEM lane), registers = 16 consecutive hidden units
+    const int quarter = warp_idx & 3;
+    const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    float* dst_row = args.S_vh + (size_t)min(row, args.nV - 1) * args.nH;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 16; ++c) {
+      const int col0 = n_blk * BLOCK_N + c * 16;
+      if (col0 >= args.nH) break;   // warp-uniform
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 16), r);
+      tmem_ld_wait();
+      if (row < args.nV) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (col0 + j < args.nH && r[j] != 0u) atomicAdd(dst_row + col0 + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+  }
+}
+
+// S[c] += sum_b X[b, c] over this block's rows; X is a bf16 {0,1} state tile [rows, ld].
+// A warp reads 256 consecutive units of one chain (16 B per lane); the eight warps of a block take
+// different chains; integer-valued partial sums are combined in shared memory, then one atomic per unit.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t B, int ld, int n, int64_t rows_per_block,
+                   float* __restrict__ S) {
+  __shared__ float red[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < B ? r0 + rows_per_block : B;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < ld) {
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(X + r * ld + c0));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += __uint_as_float(w[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    if (s != 0.f) atomicAdd(S + c, s);
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -1001,6 +1205,47 @@ int launch_multistep(const CUtensorMap* tm, const MultiArgs& a, int m_tiles, int
   return check_launch("umma_multistep_kernel");
 }
 
+template <int BLOCK_N>
+int launch_stats(const CUtensorMap& tv, const CUtensorMap& th, const StatsArgs& a, int grid, cudaStream_t st) {
+  auto kern = umma_stats_kernel<BLOCK_N>;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  if ((rc = ensure_dynamic_smem(kern, di.device, stats_smem_bytes<BLOCK_N>()))) return rc;
+  kern<<<(unsigned)grid, kStatsThreads, stats_smem_bytes<BLOCK_N>(), st>>>(tv, th, a);
+  return check_launch("umma_stats_kernel");
+}
+
+// Raw counts of the final (v, h) pair of this call's chains, ADDED to S_vh [nV, nH], S_v [nV], S_h [nH].
+int umma_stats(const Plan& pl, const __nv_bfloat16* Vs, const __nv_bfloat16* Hs, int64_t B, float* S_vh, float* S_v,
+               float* S_h, int sm_count, cudaStream_t st) {
+  RBM_REQUIRE(B <= (int64_t)1 << 24, RBM_B200_ERR_INVALID,
+              "fused statistics count in fp32: at most 2^24 chains per call (got %lld)", (long long)B);
+  int rc;
+  CUtensorMap tv, th;
+  // B rows: the padding chains read as zeros
+  if ((rc = make_tmap(&tv, Vs, (uint64_t)B, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&th, Hs, (uint64_t)B, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
+  const int bn = round_up(pl.nHp, 128) < round_up(pl.nHp, 256) ? 128 : 256;
+  StatsArgs a{};
+  a.S_vh = S_vh; a.nV = pl.nV; a.nH = pl.nH;
+  const int tiles_m = ceil_div(pl.nV, BLOCK_M);
+  a.tiles_n = ceil_div(pl.nH, bn);
+  a.tiles = tiles_m * a.tiles_n;
+  a.k_blocks = (int)ceil_div64(B, BLOCK_K);
+  // split the chains so that one wave of CTAs covers the GPU; every split owns at least one K block
+  int splits = std::max(1, std::min(a.k_blocks, sm_count / a.tiles));
+  a.kb_per_split = ceil_div(a.k_blocks, splits);
+  splits = ceil_div(a.k_blocks, a.kb_per_split);
+  rc = bn == 256 ? launch_stats<256>(tv, th, a, a.tiles * splits, st) : launch_stats<128>(tv, th, a, a.tiles * splits, st);
+  if (rc) return rc;
+  const int64_t rows_per_block = std::max<int64_t>(64, ceil_div64(B, 4 * sm_count));
+  const unsigned row_blocks = (unsigned)ceil_div64(B, rows_per_block);
+  colsum_bf16_kernel<<<dim3((unsigned)ceil_div(pl.nVp, 256), row_blocks), 256, 0, st>>>(Vs, B, pl.nVp, pl.nV, rows_per_block, S_v);
+  colsum_bf16_kernel<<<dim3((unsigned)ceil_div(pl.nHp, 256), row_blocks), 256, 0, st>>>(Hs, B, pl.nHp, pl.nH, rows_per_block, S_h);
+  return check_launch("colsum_bf16_kernel");
+}
+
 }  // namespace
 
 bool umma_variant_supported(int nV, int nH) { return nV >= 1 && nH >= 1 && nV <= 16384 && nH <= 16384; }
@@ -1009,7 +1254,7 @@ size_t umma_workspace_bytes(int nV, int nH, int64_t B) { return make_plan(nV, nH
 
 int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains,
                      uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws, size_t ws_bytes,
-                     cudaStream_t st) {
+                     cudaStream_t st, float* S_vh, float* S_v, float* S_h) {
   const Plan pl = make_plan(p->n_visible, p->n_hidden, B);
   RBM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, RBM_B200_ERR_WORKSPACE,
               "UMMA variant needs %zu bytes of workspace, got %zu", pl.total, ws_bytes);
@@ -1038,7 +1283,7 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   }
   // initial state
   if (init_chains) {
-    const int64_t n = pl.rows_pad * (pl.nVp / 8);
+    const int64_t n = pl.rows_pad * (pl.nVp / 32);
     init_chains_bf16_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(Vs, pl.rows_pad, pl.nV, pl.nVp,
                                                                          make_draw_ctx(seed, step_offset, TAG_INIT), chain_offset);
   } else {
@@ -1128,11 +1373,19 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
       if (rc) return rc;
     }
   }
+  // negative-phase statistics of the final (v, h), on the tensor cores, from the bf16 state tiles
+  if (S_vh != nullptr && k > 0) {
+    if ((rc = umma_stats(pl, Vs, Hs, B, S_vh, S_v, S_h, sm_count, st))) return rc;
+  }
   // back to the reference's dtype
   {
     const int64_t nv = B * pl.nV, nh = B * pl.nH;
-    bf16_to_f32_crop<<<(unsigned)ceil_div64(nv, 256), 256, 0, st>>>(Vs, v, B, pl.nV, pl.nVp);
-    if (k > 0) bf16_to_f32_crop<<<(unsigned)ceil_div64(nh, 256), 256, 0, st>>>(Hs, h, B, pl.nH, pl.nHp);
+    if (pl.nV % 8 == 0 && ((uintptr_t)v & 15) == 0) bf16_to_f32_crop8<<<(unsigned)ceil_div64(nv / 8, 256), 256, 0, st>>>(Vs, v, B, pl.nV, pl.nVp);
+    else bf16_to_f32_crop<<<(unsigned)ceil_div64(nv, 256), 256, 0, st>>>(Vs, v, B, pl.nV, pl.nVp);
+    if (k > 0) {
+      if (pl.nH % 8 == 0 && ((uintptr_t)h & 15) == 0) bf16_to_f32_crop8<<<(unsigned)ceil_div64(nh / 8, 256), 256, 0, st>>>(Hs, h, B, pl.nH, pl.nHp);
+      else bf16_to_f32_crop<<<(unsigned)ceil_div64(nh, 256), 256, 0, st>>>(Hs, h, B, pl.nH, pl.nHp);
+    }
   }
   return check_launch("umma output conversion");
 }

@@ -41,9 +41,12 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
 // gibbs_umma.cu — tcgen05/TMEM GEMM per half-step fed by TMA
 bool umma_variant_supported(int nV, int nH);
 size_t umma_workspace_bytes(int nV, int nH, int64_t B);
+// S_vh/S_v/S_h non-null: raw counts of the final (v, h) are ADDED to them (tensor-core V^T H over the
+// bf16 state tiles, split over the chains); the caller zeroes before and scales after, as for the SMEM variant.
 int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains,
                      uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws,
-                     size_t ws_bytes, cudaStream_t st);
+                     size_t ws_bytes, cudaStream_t st, float* S_vh = nullptr, float* S_v = nullptr,
+                     float* S_h = nullptr);
 
 size_t umma_ais_workspace_bytes(int nV, int nH, int64_t M);
 int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n_betas, uint64_t seed,

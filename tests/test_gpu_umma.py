@@ -84,6 +84,32 @@ def test_umma_many_tiles_per_cta_and_statistics():
     assert (v[-256:][clean] == ov[clean]).all() and (h[-256:][clean] == oh[clean]).all()
 
 
+@pytest.mark.parametrize("nV,nH,B,k", [(1024, 1024, 4096 + 37, 1), (200, 200, 500, 2), (784, 128, 300, 1),
+                                       (64, 64, 128, 1), (130, 700, 20001, 1), (320, 256, 70000, 1)])
+def test_umma_statistics_on_the_tensor_cores(nV, nH, B, k):
+    """rbm_b200_block_gibbs_stats on the UMMA variant: <vh> is a tcgen05 GEMM V^T H over the bf16 state tiles
+    (both operands MN-major, chains split over CTAs), <v>/<h> are column sums of the same tiles.  Binary states
+    make the raw counts integers, so they must equal the statistics of the returned (v, h) EXACTLY
+    (autograd of GumBolt.energy_exp, gumbolt.py:109-134)."""
+    W, a, c = rand_params(nV, nH, 0.05, nV + 3 * nH)
+    rbm = make_rbm(W, a, c)
+    s = divae_b200.PCD(batch_size=B, RBM=rbm, n_gibbs_sampling_steps=k, seed=29, variant="umma")
+    v, h, (S, sv, sh), e = s.block_gibbs_sampling(_stats_scale=1.0)
+    vt, ht = v.double(), h.double()
+    assert torch.equal(S.double(), vt.t() @ ht)
+    assert torch.equal(sv.double(), vt.sum(0)) and torch.equal(sh.double(), ht.sum(0))
+    # the samples are the ordinary ones
+    v2, h2 = run(W, a, c, B, k, seed=29)
+    assert (v.cpu().numpy() == v2).all() and (h.cpu().numpy() == h2).all()
+    # scaled statistics + energy expectation through negative_phase()
+    s3 = divae_b200.PCD(batch_size=B, RBM=rbm, n_gibbs_sampling_steps=k, seed=29, variant="umma")
+    e3, (S3, sv3, sh3) = s3.negative_phase()
+    torch.testing.assert_close(S3.double(), vt.t() @ ht / B, rtol=1e-6, atol=1e-7)
+    ref = -(((vt @ torch.from_numpy(W).double().to(vt.device)) * ht).sum(1) + vt @ torch.from_numpy(a).double().to(vt.device)
+            + ht @ torch.from_numpy(c).double().to(vt.device)).mean()
+    assert abs(e3.item() - ref.item()) <= 1e-4 * max(1.0, abs(ref.item()))
+
+
 def test_umma_persistent_state_and_given_v0():
     W, a, c = rand_params(128, 128, 0.2, 11)
     rbm = make_rbm(W, a, c)
