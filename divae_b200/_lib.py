@@ -28,7 +28,29 @@ class RbmParams(ctypes.Structure):
     ]
 
 
+class Linear(ctypes.Structure):
+    """rbm_b200_linear (include/rbm_b200.h): one nn.Linear, torch layout."""
+    _fields_ = [
+        ("in_features", ctypes.c_int32),
+        ("out_features", ctypes.c_int32),
+        ("weight", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p),
+    ]
+
+
+class Decoder(ctypes.Structure):
+    """rbm_b200_decoder (include/rbm_b200.h): trunk + zero or two heads."""
+    _fields_ = [
+        ("n_trunk", ctypes.c_int32),
+        ("n_head", ctypes.c_int32),
+        ("trunk", ctypes.POINTER(Linear)),
+        ("head_hits", ctypes.POINTER(Linear)),
+        ("head_act", ctypes.POINTER(Linear)),
+    ]
+
+
 _P = ctypes.POINTER(RbmParams)
+_D = ctypes.POINTER(Decoder)
 _vp, _i32, _i64, _u64, _f32, _sz, _int = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64,
                                           ctypes.c_float, ctypes.c_size_t, ctypes.c_int)
 
@@ -53,6 +75,8 @@ PROTOTYPES = {
                                  _vp, _vp, _sz, _vp]),
     "rbm_b200_ais_workspace": (_sz, [_i32, _i32, _i64]),
     "rbm_b200_ais_run": (_int, [_P, _i64, ctypes.POINTER(ctypes.c_double), _i32, _u64, _u64, _vp, _vp, _sz, _vp]),
+    "rbm_b200_decoder_workspace": (_sz, [_D, _i64]),
+    "rbm_b200_decoder_forward": (_int, [_D, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _u64, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -324,4 +324,20 @@ int rbm_b200_ais_run(const rbm_b200_params* p, int64_t n_chains, const double* b
                       (cudaStream_t)stream);
 }
 
+size_t rbm_b200_decoder_workspace(const rbm_b200_decoder* d, int64_t B) {
+  if (d == nullptr || B < 0) return 0;
+  return umma_decoder_workspace_bytes(d, B);
+}
+
+int rbm_b200_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, float* out_hits, float* out_act,
+                             float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  RBM_REQUIRE(d != nullptr, RBM_B200_ERR_INVALID, "decoder description is NULL");
+  RBM_REQUIRE(B >= 0, RBM_B200_ERR_INVALID, "negative batch");
+  int rc = require_device();
+  if (rc) return rc;
+  return umma_decoder_forward(d, x, B, out_hits, out_act, samples, seed, chain_offset, step, workspace,
+                              workspace_bytes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -226,10 +226,20 @@ struct HalfStepArgs {
   int wpart_ld;
   int debug_mode;          // profiling only (env RBM_B200_DEBUG_MODE): 1 = skip epilogue math, 2 = skip TMA+MMA
   uint32_t kf_magic;       // kKfMagic, passed at run time (see EpiParams)
+  // linear (decoder) epilogues only
+  int relu;                // max(0, .) after the bias
+  int lo_off;              // EPI_LINEAR_SPLIT: column offset of the low-part tile inside the output buffer
+  float* out_f32;          // EPI_LINEAR_F32: [rows_valid, ld_out] fp32 destination
+  int ld_out;
+  const uint16_t* mask;    // EPI_LINEAR_F32: optional {0,1} bf16 gate [rows, ld_mask] multiplied into the output
+  int ld_mask;
+  int64_t rows_valid;      // EPI_LINEAR_F32: rows >= rows_valid are padding and are not stored
 };
 
 // Epilogue flavours
-enum { EPI_GIBBS = 0, EPI_ANNEALED = 1, EPI_AIS_WEIGHT = 2 };
+enum { EPI_GIBBS = 0, EPI_ANNEALED = 1, EPI_AIS_WEIGHT = 2,
+       EPI_LINEAR_SPLIT = 3,   // y = act(acc + bias) stored as bf16 high part + bf16 low part (next layer's A operand)
+       EPI_LINEAR_F32 = 4 };   // y = act(acc + bias) [* gate] stored as fp32
 
 __device__ __forceinline__ float lg2_approx(float x) {
   float y;
@@ -278,6 +288,13 @@ struct EpiParams {
   // 0x4B000000 (float 2^23) handed over as a RUN-TIME value: as a literal, ptxas encodes it as PRMT's
   // immediate and then has to materialise the byte selector in a register before every PRMT
   uint32_t kf_magic;
+  // linear flavours (see HalfStepArgs)
+  int relu, lo_off;
+  float* out_f32;
+  int ld_out;
+  const uint16_t* mask;
+  int ld_mask;
+  int64_t rows_valid;
 };
 
 // Epilogue of ONE 128 x BLOCK_N tile for one warp: TMEM -> decisions -> swizzled smem box -> TMA store.
@@ -405,7 +422,110 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
     }
 }
 
-template <int BLOCK_N, bool B_MN_MAJOR, int EPI, int CTAS>
+
+// Linear-layer epilogues of ONE 128 x BLOCK_N tile for one warp (decoder path):
+//   EPI_LINEAR_SPLIT  y = act(acc + bias) -> bf16 high part and bf16 low part (y - high), two TMA-stored boxes;
+//                     [high | high | low] x [W_high | W_low | W_high] in the next layer's GEMM keeps fp32-grade accuracy
+//   EPI_LINEAR_F32    y = act(acc + bias) [* gate] -> fp32, stored straight from registers (64 B per lane and span)
+template <int BLOCK_N, int EPI, class WaitFn, class ReleaseFn>
+__device__ __forceinline__ void epilogue_tile_linear(const EpiParams& ep, const CUtensorMap* tmap_out, uint32_t tmem_acc,
+                                                     int n_blk, int row_base, int quarter, int cq, int lane,
+                                                     uint32_t stage_warp, WaitFn wait_full, ReleaseFn release) {
+  constexpr int kColsPerWarp = BLOCK_N / kEpiSets;
+  constexpr int kGroups = kColsPerWarp / 32;
+  const uint32_t stage_row = stage_warp + (uint32_t)lane * 64u;
+  const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+  const int64_t row = (int64_t)row_base + lane;
+  wait_full();
+  tcgen05_fence_after();
+#pragma unroll 1
+  for (int g = 0; g < kGroups; ++g) {
+    const int col_in_tile = cq * kColsPerWarp + g * 32;
+    const int col0 = n_blk * BLOCK_N + col_in_tile;
+    const bool live = col0 < ep.ldo;
+    uint32_t hi[16], lo[16];   // EPI_LINEAR_SPLIT: the 32 units of this group as bf16 pairs
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t r[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(col_in_tile + 16 * hh), r);
+      tmem_ld_wait();
+      if (g == kGroups - 1 && hh == 1) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) release();
+      }
+      if (!live) continue;
+      float y[16];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.nbias + col0 + 16 * hh) + q4);
+        y[4 * q4 + 0] = __uint_as_float(r[4 * q4 + 0]) + b4.x;
+        y[4 * q4 + 1] = __uint_as_float(r[4 * q4 + 1]) + b4.y;
+        y[4 * q4 + 2] = __uint_as_float(r[4 * q4 + 2]) + b4.z;
+        y[4 * q4 + 3] = __uint_as_float(r[4 * q4 + 3]) + b4.w;
+      }
+      if (ep.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+      }
+      if (EPI == EPI_LINEAR_SPLIT) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(y[j]), h1 = __float2bfloat16_rn(y[j + 1]);
+          const __nv_bfloat16 l0 = __float2bfloat16_rn(y[j] - __bfloat162float(h0));
+          const __nv_bfloat16 l1 = __float2bfloat16_rn(y[j + 1] - __bfloat162float(h1));
+          hi[8 * hh + (j >> 1)] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          lo[8 * hh + (j >> 1)] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+      } else {
+        const int cbase = col0 + 16 * hh;
+        if (row < ep.rows_valid && cbase < ep.n_valid) {
+          if (ep.mask != nullptr) {
+            const uint4* mp = reinterpret_cast<const uint4*>(ep.mask + row * ep.ld_mask + cbase);
+            const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              y[j] *= __uint_as_float(mw[j >> 1] << 16);
+              y[j + 1] *= __uint_as_float(mw[j >> 1] & 0xFFFF0000u);
+            }
+          }
+          float* dst = ep.out_f32 + row * ep.ld_out + cbase;
+          if ((ep.ld_out & 3) == 0 && cbase + 16 <= ep.n_valid && (reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              reinterpret_cast<float4*>(dst)[q4] = make_float4(y[4 * q4], y[4 * q4 + 1], y[4 * q4 + 2], y[4 * q4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cbase + j < ep.n_valid) dst[j] = y[j];
+          }
+        }
+      }
+    }
+    if (EPI == EPI_LINEAR_SPLIT && live) {
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        // the previous TMA store of this warp must have finished READING the staging box
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        const uint32_t* pk = part == 0 ? hi : lo;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+          st_shared_v4(stage_row + (((uint32_t)ch ^ sw) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmap_out, stage_warp, (part == 0 ? 0 : ep.lo_off) + col0, row_base);
+          tma_store_commit();
+        }
+      }
+    }
+  }
+}
+
+// SPLIT3: the A operand is [high | low] column blocks read as [high | high | low] (decoder path)
+template <int BLOCK_N, bool B_MN_MAJOR, int EPI, int CTAS, bool SPLIT3 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const HalfStepArgs args) {
@@ -473,10 +593,12 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * L::kStageBytes;
           const uint32_t sb = sa + kABytes;
+          // SPLIT3: K blocks [0,n) and [n,2n) read the high part, [2n,3n) the low part stored behind it
+          const int ka = (SPLIT3 && kb >= args.k_blocks / 3) ? kb - args.k_blocks / 3 : kb;
           if (elect_one_sync()) {
             if (CTAS == 1) {
               mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
-              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, row0);
+              tma_load_2d(sa, &tmap_a, full_bar(stage), ka * BLOCK_K, row0);
               if (B_MN_MAJOR) {
                 // W[k rows][n cols]: one [64 x 64] box per 64-column MN block, 8 KB apart (LBO)
 #pragma unroll
@@ -491,7 +613,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
               const uint32_t lead_full = mapa_u32(full_bar(stage), 0);
               if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * L::kStageBytes);
               else mbar_arrive_cluster(lead_full);
-              tma_load_2d_pair(sa, &tmap_a, lead_full, kb * BLOCK_K, row0);
+              tma_load_2d_pair(sa, &tmap_a, lead_full, ka * BLOCK_K, row0);
               if (B_MN_MAJOR) {
 #pragma unroll
                 for (int nb = 0; nb < kBCols / 64; ++nb)
@@ -565,13 +687,19 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       ep.nbias = args.nbias; ep.ldo = args.ldo; ep.n_valid = args.n_valid; ep.ctx = args.ctx;
       ep.scale = args.scale; ep.bmul = args.bmul; ep.ratio = args.ratio; ep.debug_mode = args.debug_mode;
       ep.kf_magic = args.kf_magic;
-      epilogue_tile<BLOCK_N, EPI>(
-          ep, &tmap_out, tmem_base + (uint32_t)(as * BLOCK_N), n_blk, row_base, chain, quarter, cq, lane, stage_warp, wsum,
-          [&] { mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u); },
-          [&] {
-            if (CTAS == 2) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(as), 0));   // the leader's barrier
-            else mbar_arrive(tmem_empty_bar(as));
-          });
+      ep.relu = args.relu; ep.lo_off = args.lo_off; ep.out_f32 = args.out_f32; ep.ld_out = args.ld_out;
+      ep.mask = args.mask; ep.ld_mask = args.ld_mask; ep.rows_valid = args.rows_valid;
+      auto wait_full = [&] { mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u); };
+      auto release = [&] {
+        if (CTAS == 2) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(as), 0));   // the leader's barrier
+        else mbar_arrive(tmem_empty_bar(as));
+      };
+      if constexpr (EPI == EPI_LINEAR_SPLIT || EPI == EPI_LINEAR_F32)
+        epilogue_tile_linear<BLOCK_N, EPI>(ep, &tmap_out, tmem_base + (uint32_t)(as * BLOCK_N), n_blk, row_base, quarter,
+                                           cq, lane, stage_warp, wait_full, release);
+      else
+        epilogue_tile<BLOCK_N, EPI>(ep, &tmap_out, tmem_base + (uint32_t)(as * BLOCK_N), n_blk, row_base, chain, quarter,
+                                    cq, lane, stage_warp, wsum, wait_full, release);
       if (EPI == EPI_AIS_WEIGHT) {
         // exactly one thread owns (row, slot) in a launch: plain read-modify-write, deterministic
         float* slot_ptr = args.wpart + (size_t)row * args.wpart_ld + (n_blk * kEpiSets + cq);
@@ -1132,10 +1260,10 @@ Plan make_plan(int nV, int nH, int64_t B) {
   return p;
 }
 
-template <int BLOCK_N, bool B_MN_MAJOR, int EPI, int CTAS>
+template <int BLOCK_N, bool B_MN_MAJOR, int EPI, int CTAS, bool SPLIT3 = false>
 int launch_half_step_impl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HalfStepArgs& a,
                           int sm_count, cudaStream_t st) {
-  auto kern = umma_half_step_kernel<BLOCK_N, B_MN_MAJOR, EPI, CTAS>;
+  auto kern = umma_half_step_kernel<BLOCK_N, B_MN_MAJOR, EPI, CTAS, SPLIT3>;
   using L = SmemLayout<BLOCK_N, CTAS>;
   {
     DeviceInfo di;
@@ -1246,7 +1374,245 @@ int umma_stats(const Plan& pl, const __nv_bfloat16* Vs, const __nv_bfloat16* Hs,
   return check_launch("colsum_bf16_kernel");
 }
 
+
+// ===================================================================================================
+// Decoder MLP on generated prior samples: the step right after the sampler in
+// shower / image generation (models/autoencoders/gumboltCaloV5.py:78-96, dvaepp.py:214-225) -
+//   BasicDecoder   (models/networks/basicCoders.py:28-42): chain of nn.Linear, ReLU between, last layer linear
+//   BasicDecoderV3 (basicCoders.py:63-84): shared trunk (_layers, all ReLU), two heads (_layers2 hits, _layers3
+//                  activations), last head layer linear
+//   shower tail    sample = relu(activations) * heaviside(hits + logit(rho)) (gumboltCaloV5.py:91-93,
+//                  utils/dists/gumbelmod.py:18-24) = relu(activations) * [sigmoid(hits) >= u], u = 1 - rho
+// Every layer is one launch of the SAME tcgen05 kernel as a Gibbs half-step (A = activations K-major, B = the
+// nn.Linear weight [out, in], which already is K-major).  fp32-grade accuracy on bf16 tensor cores: activations
+// and weights are split x = x_hi + x_lo (both bf16) and the GEMM runs over the tripled K axis
+//   [x_hi | x_hi | x_lo] . [W_hi | W_lo | W_hi]^T = x_hi W_hi + x_hi W_lo + x_lo W_hi      (error ~2^-16 relative),
+// accumulated in fp32 in TMEM.  Hidden layers store [high | low] bf16 tiles for the next layer (EPI_LINEAR_SPLIT),
+// the hits head ends in the Gibbs epilogue itself (sigmoid + Philox + compare, TAG_HITS) and the activation head
+// multiplies that gate into relu(acc + bias) on its way to the fp32 output (EPI_LINEAR_F32).
+constexpr uint32_t TAG_HITS = 4;   // Philox tag of the hit draws (oracle/philox.py)
+
+__global__ void split_input_kernel(const float* __restrict__ x, int64_t B, int n, uint16_t* __restrict__ dst,
+                                   int64_t rows_pad, int Kp) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_pad * Kp) return;
+  const int64_t r = idx / Kp;
+  const int c = (int)(idx % Kp);
+  const float val = (r < B && c < n) ? x[r * n + c] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
+  dst[r * (2 * (int64_t)Kp) + c] = __bfloat16_as_ushort(hi);
+  dst[r * (2 * (int64_t)Kp) + Kp + c] = __bfloat16_as_ushort(lo);
+}
+// W [N, K] fp32 -> [Np, 3 Kp] bf16 = [W_hi | W_lo | W_hi], zero padded
+__global__ void split_weight_kernel(const float* __restrict__ W, int N, int K, uint16_t* __restrict__ dst, int Np, int Kp) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Np * Kp) return;
+  const int r = (int)(idx / Kp), c = (int)(idx % Kp);
+  const float val = (r < N && c < K) ? W[(int64_t)r * K + c] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
+  uint16_t* row = dst + (int64_t)r * (3 * Kp);
+  row[c] = __bfloat16_as_ushort(hi);
+  row[Kp + c] = __bfloat16_as_ushort(lo);
+  row[2 * Kp + c] = __bfloat16_as_ushort(hi);
+}
+__global__ void pad_bias_kernel(const float* __restrict__ bias, float* __restrict__ dst, int n, int n_pad, float mul) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) dst[i] = i < n ? mul * bias[i] : 0.f;
+}
+
+struct LayerPlan {
+  const rbm_b200_linear* lin;
+  int Kp, Np, bn;
+  size_t off_W, off_bias, off_out;   // off_out: [rows_pad, 2 Np] bf16 (hidden layers)
+};
+struct DecoderPlan {
+  std::vector<LayerPlan> trunk, hits, act;
+  int64_t rows_pad;
+  int n_out, Np_out;
+  size_t off_in, off_mask, off_nbias_hits, total;
+};
+
+int make_decoder_plan(const rbm_b200_decoder* d, int64_t B, DecoderPlan* out) {
+  RBM_REQUIRE(d != nullptr && d->n_trunk >= 1 && d->trunk != nullptr, RBM_B200_ERR_INVALID, "decoder needs at least one trunk layer");
+  RBM_REQUIRE(d->n_head >= 0 && (d->n_head == 0 || d->head_act != nullptr), RBM_B200_ERR_INVALID, "decoder head description is incomplete");
+  DecoderPlan& pl = *out;
+  pl.rows_pad = ceil_div64(std::max<int64_t>(B, 1), 2 * BLOCK_M) * (2 * BLOCK_M);
+  auto align = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  size_t o = 0;
+  auto add_chain = [&](const rbm_b200_linear* ls, int n, int in_features, std::vector<LayerPlan>& dst) -> int {
+    int prev = in_features;
+    for (int i = 0; i < n; ++i) {
+      const rbm_b200_linear& l = ls[i];
+      RBM_REQUIRE(l.in_features >= 1 && l.out_features >= 1 && l.in_features <= 16384 && l.out_features <= 16384,
+                  RBM_B200_ERR_INVALID, "layer shape %d -> %d out of range", l.in_features, l.out_features);
+      RBM_REQUIRE(l.in_features == prev, RBM_B200_ERR_INVALID, "size mismatch: layer expects %d inputs, previous layer has %d",
+                  l.in_features, prev);
+      RBM_REQUIRE(l.weight != nullptr && l.bias != nullptr, RBM_B200_ERR_INVALID, "layer parameter pointer is NULL");
+      LayerPlan lp;
+      lp.lin = &l;
+      lp.Kp = round_up(l.in_features, 64); lp.Np = round_up(l.out_features, 64);
+      lp.bn = pick_block_n(lp.Np, pl.rows_pad);
+      lp.off_W = o; o = align(o + (size_t)lp.Np * 3 * lp.Kp * 2);
+      lp.off_bias = o; o = align(o + (size_t)round_up(lp.Np, 256) * 4);
+      lp.off_out = o; o = align(o + (size_t)pl.rows_pad * 2 * lp.Np * 2);
+      dst.push_back(lp);
+      prev = l.out_features;
+    }
+    return 0;
+  };
+  int rc = add_chain(d->trunk, d->n_trunk, d->trunk[0].in_features, pl.trunk);
+  if (rc) return rc;
+  const int trunk_out = d->trunk[d->n_trunk - 1].out_features;
+  pl.n_out = trunk_out;
+  if (d->n_head > 0) {
+    if (d->head_hits && (rc = add_chain(d->head_hits, d->n_head, trunk_out, pl.hits))) return rc;
+    if ((rc = add_chain(d->head_act, d->n_head, trunk_out, pl.act))) return rc;
+    pl.n_out = d->head_act[d->n_head - 1].out_features;
+    RBM_REQUIRE(!d->head_hits || d->head_hits[d->n_head - 1].out_features == pl.n_out, RBM_B200_ERR_INVALID,
+                "size mismatch: the two heads end in %d and %d units", d->head_hits[d->n_head - 1].out_features, pl.n_out);
+  }
+  pl.Np_out = round_up(pl.n_out, 64);
+  const int K0p = round_up(d->trunk[0].in_features, 64);
+  pl.off_in = o; o = align(o + (size_t)pl.rows_pad * 2 * K0p * 2);
+  pl.off_mask = o; o = align(o + (size_t)pl.rows_pad * pl.Np_out * 2);
+  pl.off_nbias_hits = o; o = align(o + (size_t)round_up(pl.Np_out, 256) * 4);
+  pl.total = o + 1024;
+  return 0;
+}
+
+template <int EPI>
+int launch_linear(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HalfStepArgs& a,
+                  int sm_count, cudaStream_t st) {
+  return bn == 256 ? launch_half_step_impl<256, false, EPI, 1, true>(ta, tb, to, a, sm_count, st)
+                   : launch_half_step_impl<128, false, EPI, 1, true>(ta, tb, to, a, sm_count, st);
+}
+
 }  // namespace
+
+size_t umma_decoder_workspace_bytes(const rbm_b200_decoder* d, int64_t B) {
+  DecoderPlan pl;
+  if (make_decoder_plan(d, B, &pl)) return 0;
+  return pl.total;
+}
+
+int umma_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, float* out_hits, float* out_act,
+                         float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+  DecoderPlan pl;
+  int rc = make_decoder_plan(d, B, &pl);
+  if (rc) return rc;
+  RBM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, RBM_B200_ERR_WORKSPACE,
+              "decoder needs %zu bytes of workspace, got %zu", pl.total, ws_bytes);
+  RBM_REQUIRE(samples == nullptr || !pl.hits.empty(), RBM_B200_ERR_INVALID,
+              "shower samples need both heads (hits and activations)");
+  RBM_REQUIRE(out_hits == nullptr || !pl.hits.empty(), RBM_B200_ERR_INVALID, "there is no hits head to output");
+  if (B == 0) return 0;
+  RBM_REQUIRE(x != nullptr, RBM_B200_ERR_INVALID, "input pointer is NULL");
+  DeviceInfo di;
+  if ((rc = get_device_info(&di))) return rc;
+  RBM_REQUIRE(di.cc_major == 10, RBM_B200_ERR_NO_DEVICE, "the decoder path needs an sm_100 device (got cc %d.x)", di.cc_major);
+  const int sm_count = di.sm_count;
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  const int in_features = d->trunk[0].in_features;
+  const int K0p = round_up(in_features, 64);
+  uint16_t* A0 = reinterpret_cast<uint16_t*>(base + pl.off_in);
+  uint16_t* mask = reinterpret_cast<uint16_t*>(base + pl.off_mask);
+  float* nbias_hits = reinterpret_cast<float*>(base + pl.off_nbias_hits);
+
+  // stage: split input, split weights, padded biases
+  {
+    const int64_t n = pl.rows_pad * K0p;
+    split_input_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, B, in_features, A0, pl.rows_pad, K0p);
+  }
+  auto stage_chain = [&](const std::vector<LayerPlan>& ch) {
+    for (const LayerPlan& lp : ch) {
+      const int64_t n = (int64_t)lp.Np * lp.Kp;
+      split_weight_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(lp.lin->weight, lp.lin->out_features, lp.lin->in_features,
+                                                                     reinterpret_cast<uint16_t*>(base + lp.off_W), lp.Np, lp.Kp);
+      const int np256 = round_up(lp.Np, 256);
+      pad_bias_kernel<<<ceil_div(np256, 256), 256, 0, st>>>(lp.lin->bias, reinterpret_cast<float*>(base + lp.off_bias),
+                                                           lp.lin->out_features, np256, 1.f);
+    }
+  };
+  stage_chain(pl.trunk); stage_chain(pl.hits); stage_chain(pl.act);
+  if (samples != nullptr) {
+    const LayerPlan& lp = pl.hits.back();
+    const int np256 = round_up(lp.Np, 256);
+    pad_bias_kernel<<<ceil_div(np256, 256), 256, 0, st>>>(lp.lin->bias, nbias_hits, lp.lin->out_features, np256,
+                                                         -1.4426950408889634f);
+  }
+  if ((rc = check_launch("decoder staging kernels"))) return rc;
+
+  // one layer = one launch.  mode: 0 hidden (split bf16 out), 1 fp32 out, 2 hit gate (Gibbs epilogue), 3 gated shower
+  auto run_layer = [&](const LayerPlan& lp, const uint16_t* A, int Kp_in, int mode, float* dst_f32) -> int {
+    CUtensorMap ta, tb, to;
+    int r;
+    if ((r = make_tmap(&ta, A, (uint64_t)pl.rows_pad, (uint64_t)(2 * Kp_in), (uint64_t)(2 * Kp_in), BLOCK_M))) return r;
+    if ((r = make_tmap(&tb, base + lp.off_W, (uint64_t)lp.Np, (uint64_t)(3 * lp.Kp), (uint64_t)(3 * lp.Kp), (uint32_t)lp.bn))) return r;
+    HalfStepArgs a{};
+    a.nbias = reinterpret_cast<const float*>(base + lp.off_bias);
+    a.ldo = lp.Np; a.m_tiles = (int)(pl.rows_pad / BLOCK_M); a.n_tiles = ceil_div(lp.Np, lp.bn);
+    a.k_blocks = 3 * lp.Kp / BLOCK_K; a.n_valid = lp.lin->out_features; a.chain_offset = chain_offset;
+    a.rows_valid = B;
+    if (mode == 0) {
+      uint16_t* out = reinterpret_cast<uint16_t*>(base + lp.off_out);
+      if ((r = make_tmap(&to, out, (uint64_t)pl.rows_pad, (uint64_t)(2 * lp.Np), (uint64_t)(2 * lp.Np), 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+      a.relu = 1; a.lo_off = lp.Np;
+      return launch_linear<EPI_LINEAR_SPLIT>(lp.bn, ta, tb, to, a, sm_count, st);
+    }
+    if (mode == 2) {
+      if ((r = make_tmap(&to, mask, (uint64_t)pl.rows_pad, (uint64_t)lp.Np, (uint64_t)lp.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+      a.nbias = nbias_hits;
+      a.ctx = make_draw_ctx(seed, step, TAG_HITS);
+      return launch_linear<EPI_GIBBS>(lp.bn, ta, tb, to, a, sm_count, st);
+    }
+    a.out_f32 = dst_f32; a.ld_out = lp.lin->out_features;
+    a.relu = mode == 3 ? 1 : 0;
+    a.mask = mode == 3 ? mask : nullptr; a.ld_mask = lp.Np;
+    return launch_linear<EPI_LINEAR_F32>(lp.bn, ta, tb, ta, a, sm_count, st);   // no TMA store: any valid map
+  };
+
+  // trunk
+  const uint16_t* cur = A0;
+  int cur_Kp = K0p;
+  const bool single = pl.act.empty();
+  for (size_t i = 0; i < pl.trunk.size(); ++i) {
+    const LayerPlan& lp = pl.trunk[i];
+    if (single && i + 1 == pl.trunk.size()) {
+      // BasicDecoder: the last layer is linear (output_activation_fct = Identity, basicCoders.py:38-39)
+      if (out_act != nullptr && (rc = run_layer(lp, cur, cur_Kp, 1, out_act))) return rc;
+      return 0;
+    }
+    if ((rc = run_layer(lp, cur, cur_Kp, 0, nullptr))) return rc;
+    cur = reinterpret_cast<const uint16_t*>(base + lp.off_out); cur_Kp = lp.Np;
+  }
+  // heads
+  auto run_head = [&](const std::vector<LayerPlan>& ch, const uint16_t** last_in, int* last_Kp) -> int {
+    const uint16_t* a_in = cur; int kp = cur_Kp;
+    for (size_t i = 0; i + 1 < ch.size(); ++i) {
+      int r = run_layer(ch[i], a_in, kp, 0, nullptr);
+      if (r) return r;
+      a_in = reinterpret_cast<const uint16_t*>(base + ch[i].off_out); kp = ch[i].Np;
+    }
+    *last_in = a_in; *last_Kp = kp;
+    return 0;
+  };
+  const uint16_t* in_hits = nullptr; const uint16_t* in_act = nullptr;
+  int kp_hits = 0, kp_act = 0;
+  if (!pl.hits.empty() && (out_hits != nullptr || samples != nullptr)) {
+    if ((rc = run_head(pl.hits, &in_hits, &kp_hits))) return rc;
+    if (out_hits != nullptr && (rc = run_layer(pl.hits.back(), in_hits, kp_hits, 1, out_hits))) return rc;
+    if (samples != nullptr && (rc = run_layer(pl.hits.back(), in_hits, kp_hits, 2, nullptr))) return rc;
+  }
+  if (out_act != nullptr || samples != nullptr) {
+    if ((rc = run_head(pl.act, &in_act, &kp_act))) return rc;
+    if (out_act != nullptr && (rc = run_layer(pl.act.back(), in_act, kp_act, 1, out_act))) return rc;
+    if (samples != nullptr && (rc = run_layer(pl.act.back(), in_act, kp_act, 3, samples))) return rc;
+  }
+  return 0;
+}
 
 bool umma_variant_supported(int nV, int nH) { return nV >= 1 && nH >= 1 && nV <= 16384 && nH <= 16384; }
 

@@ -1,0 +1,134 @@
+"""Decoder MLP on generated prior samples: the step right after the sampler
+in shower / image generation.
+
+Host-side mirror of what the reference does in Python on ATen:
+
+    output_hits, output_activations = self.decoder(prior_samples)             # gumboltCaloV5.py:90
+    sample = self._energy_activation_fct(output_activations) \
+             * self._hit_smoothing_dist_mod(output_hits, beta, False)          # gumboltCaloV5.py:93
+
+`DecoderRunner` wraps a reference decoder module (BasicDecoder / BasicDecoderV3,
+models/networks/basicCoders.py:28-84 - anything exposing `_layers` [, `_layers2`, `_layers3`] of
+nn.Linear and a ReLU hidden activation) and runs it through `rbm_b200_decoder_forward`: one tcgen05
+GEMM per layer on split-bf16 operands (fp32-grade accuracy), the shower tail fused into the last two.
+`generate_samples` mirrors GumBoltCaloV5.generate_samples (gumboltCaloV5.py:78-96) on top of
+`PCD.sample` + `DecoderRunner`.  No CPU fallback: CPU modules raise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, _ops
+
+
+def _linear_list(mods, what):
+    out = []
+    for m in mods:
+        if not isinstance(m, torch.nn.Linear) or m.bias is None:
+            raise RuntimeError("divae_b200 decoder: %s must be nn.Linear layers with bias (got %r)" % (what, m))
+        out.append(m)
+    return out
+
+
+class DecoderRunner:
+    """Runs a reference decoder module's forward pass (and the shower tail) on the B200 path."""
+
+    def __init__(self, decoder):
+        act = getattr(decoder, "_activation_fct", None)
+        if act is not None and not isinstance(act, torch.nn.ReLU):
+            raise RuntimeError("divae_b200 decoder: only the ReLU hidden activation of the reference configs "
+                               "(configs/model/*.yaml: activation_fct: relu) is implemented, got %r" % (act,))
+        out_act = getattr(decoder, "_output_activation_fct", None)
+        if out_act is not None and not isinstance(out_act, torch.nn.Identity):
+            raise RuntimeError("divae_b200 decoder: output_activation_fct must be Identity (basicCoders.py:29,64), got %r"
+                               % (out_act,))
+        self._decoder = decoder
+        self._trunk = _linear_list(decoder._layers, "_layers")
+        l2, l3 = getattr(decoder, "_layers2", None), getattr(decoder, "_layers3", None)
+        self._hits = _linear_list(l2, "_layers2") if l2 is not None else []
+        self._act = _linear_list(l3, "_layers3") if l3 is not None else []
+        if len(self._hits) != len(self._act):
+            raise RuntimeError("divae_b200 decoder: the two heads must have the same depth")
+        if not self._trunk:
+            raise RuntimeError("divae_b200 decoder: BasicDecoderV2-style decoders without a shared trunk are not supported")
+        self.in_features = self._trunk[0].in_features
+        self.out_features = (self._act[-1] if self._act else self._trunk[-1]).out_features
+        self.two_heads = bool(self._act)
+
+    def _describe(self):
+        keep = []
+
+        def arr(mods):
+            if not mods:
+                return None
+            a = (_lib.Linear * len(mods))()
+            for i, m in enumerate(mods):
+                w = _ops._f32c(m.weight.detach(), "decoder weight")
+                b = _ops._f32c(m.bias.detach(), "decoder bias")
+                keep.extend((w, b))
+                a[i] = _lib.Linear(m.in_features, m.out_features, w.data_ptr(), b.data_ptr())
+            keep.append(a)
+            return a
+
+        t, h, a = arr(self._trunk), arr(self._hits), arr(self._act)
+        d = _lib.Decoder(len(self._trunk), len(self._act), t,
+                         h if h is not None else ctypes.cast(None, ctypes.POINTER(_lib.Linear)),
+                         a if a is not None else ctypes.cast(None, ctypes.POINTER(_lib.Linear)))
+        return d, keep
+
+    def _run(self, x, want_hits, want_act, want_samples, seed=0, chain_offset=0, step=0):
+        lib = _lib.load()
+        x = _ops._f32c(x, "decoder input")
+        if x.dim() != 2 or x.shape[1] != self.in_features:
+            raise RuntimeError("size mismatch: decoder expects [B, %d], got %s" % (self.in_features, tuple(x.shape)))
+        B = x.shape[0]
+        d, keep = self._describe()
+        dev = x.device
+        new = lambda: torch.empty((B, self.out_features), dtype=torch.float32, device=dev)
+        hits = new() if want_hits else None
+        act = new() if want_act else None
+        samples = new() if want_samples else None
+        with torch.no_grad(), _ops._on_device(dev):
+            n = lib.rbm_b200_decoder_workspace(ctypes.byref(d), B)
+            if n == 0 and B > 0:
+                _lib.check(-1, "decoder_workspace")
+            ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+            _lib.check(lib.rbm_b200_decoder_forward(ctypes.byref(d), _ops._ptr(x), B, _ops._ptr(hits), _ops._ptr(act),
+                                                    _ops._ptr(samples), seed, chain_offset, step, _ops._ptr(ws), n,
+                                                    _ops._stream()), "decoder_forward")
+        del keep
+        return hits, act, samples
+
+    def forward(self, x):
+        """Same return value as `decoder(x)`: a tensor (BasicDecoder) or (output_hits, output_activations)."""
+        if self.two_heads:
+            hits, act, _ = self._run(x, True, True, False)
+            return hits, act
+        return self._run(x, False, True, False)[1]
+
+    __call__ = forward
+
+    def shower(self, x, seed, chain_offset=0, step=0):
+        """relu(output_activations) * [sigmoid(output_hits) >= u] with Philox draws (gumboltCaloV5.py:93)."""
+        if not self.two_heads:
+            raise RuntimeError("divae_b200 decoder: shower samples need the two-headed decoder (BasicDecoderV3)")
+        return self._run(x, False, False, True, seed, chain_offset, step)[2]
+
+
+def generate_samples(model, num_samples=64, true_energy=None, seed=0):
+    """Drop-in for GumBoltCaloV5.generate_samples (models/autoencoders/gumboltCaloV5.py:78-96).
+
+    The reference loops `num_samples // batch_size` times over block_gibbs_sampling() + decoder; here the chains
+    of all iterations are drawn in ONE sampler launch (`PCD.sample`) and decoded in one pass.  Returns
+    (true_energies [n,1], samples [n, n_out]) with n = max(num_samples // batch_size, 1) * batch_size."""
+    sampler = model.sampler
+    bs = sampler.get_batch_size()
+    n = max(num_samples // bs, 1) * bs
+    v, h = sampler.sample(n)
+    if true_energy is None:
+        true_e = torch.rand((n, 1), device=v.device) * 100.
+    else:
+        true_e = torch.ones((n, 1), device=v.device) * true_energy
+    runner = DecoderRunner(model.decoder)
+    x = torch.cat([v, h, true_e], dim=1)
+    return true_e, runner.shower(x, seed=seed)

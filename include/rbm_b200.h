@@ -203,6 +203,46 @@ RBM_B200_API int rbm_b200_ais_run(const rbm_b200_params *p, int64_t n_chains, co
                                   int32_t n_betas, uint64_t seed, uint64_t chain_offset, double *logw,
                                   void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- next row: the decoder MLP applied to generated prior samples ------------
+ * One fully connected layer y = x W^T + b in torch.nn.Linear layout
+ * (models/networks/networks.py:33-35: nn.Linear(node[0], node[1])). */
+typedef struct rbm_b200_linear {
+  int32_t in_features, out_features;
+  const float *weight; /* [out_features, in_features] row-major fp32, device */
+  const float *bias;   /* [out_features] fp32, device */
+} rbm_b200_linear;
+
+/* A decoder: `n_trunk` shared layers, then zero or two heads of `n_head` layers each.  Hidden
+ * activation ReLU (configs/model/*.yaml: activation_fct: relu), last layer of a chain linear.
+ *   BasicDecoder   (models/networks/basicCoders.py:28-42):  n_head = 0, trunk = _layers
+ *   BasicDecoderV3 (basicCoders.py:63-84): trunk = _layers (all ReLU), head_hits = _layers2,
+ *                  head_act = _layers3
+ * The arrays of rbm_b200_linear are HOST memory; the parameters they point to are device memory. */
+typedef struct rbm_b200_decoder {
+  int32_t n_trunk, n_head;
+  const rbm_b200_linear *trunk;
+  const rbm_b200_linear *head_hits; /* NULL when there is no hits head */
+  const rbm_b200_linear *head_act;  /* NULL when n_head = 0 */
+} rbm_b200_decoder;
+
+/* Replaces `self.decoder(prior_samples)` and the shower tail of generate_samples
+ * (models/autoencoders/gumboltCaloV5.py:88-93, gumboltCalo.py:69-90, dvaepp.py:221-223):
+ *   x        [B, trunk[0].in_features] fp32: cat([rbm_vis, rbm_hid, true_e], 1) or any latent input
+ *   out_hits [B, n_out] head_hits output (logits), or NULL
+ *   out_act  [B, n_out] head_act output - or the single chain's output when n_head = 0 -, or NULL
+ *   samples  [B, n_out] relu(out_act) * [sigmoid(out_hits) >= u], or NULL: the reference's
+ *            energy_activation(output_activations) * GumbelMod(output_hits, beta, is_training=False)
+ *            (utils/dists/gumbelmod.py:18-24: heaviside(logits + log rho - log(1-rho)) with rho ~ U(0,1)
+ *            fires with probability sigmoid(logits); u = 1 - rho).  u comes from the library's Philox
+ *            contract: key seed, counter (unit block of the output unit, chain_offset + row, step, tag 4).
+ * Every layer is one tcgen05 GEMM (bf16 operands split in high + low parts, three products, fp32
+ * accumulation: relative error ~2^-16 against the fp32 reference).  Needs an sm_100 device.
+ * workspace: rbm_b200_decoder_workspace(...) bytes (0 for an invalid description). */
+RBM_B200_API size_t rbm_b200_decoder_workspace(const rbm_b200_decoder *d, int64_t B);
+RBM_B200_API int rbm_b200_decoder_forward(const rbm_b200_decoder *d, const float *x, int64_t B, float *out_hits,
+                                          float *out_act, float *samples, uint64_t seed, uint64_t chain_offset,
+                                          uint64_t step, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,9 @@ Fixtures (all small):
   cd1.npz          sandbox Contrastive_Divergence.contrastive_divergence          (rbm_standalone.py:75-121)
   negphase.npz     GumBolt.energy_exp + its autograd w.r.t. (W,a,c)               (gumbolt.py:109-134)
   port_check.npz   torch port == reference under the same torch seed (bit-exact)
+  decoder_v3.npz   BasicDecoderV3.forward + the shower tail of generate_samples with GumbelMod
+                   (basicCoders.py:63-84, gumboltCaloV5.py:88-93, gumbelmod.py:18-24)
+  decoder_basic.npz  BasicDecoder.forward (basicCoders.py:28-42)
 """
 import os
 import sys
@@ -21,7 +24,7 @@ import sys
 import numpy as np
 import torch
 
-from . import _ref_shim, philox, rbm_oracle as orc, ref_torch_port as port
+from . import _ref_shim, decoder_oracle as dec, philox, rbm_oracle as orc, ref_torch_port as port
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -218,6 +221,61 @@ def gen_port_check():
     print("port bit-identical to reference PCD")
 
 
+def _layer_arrays(mods):
+    return [(m.weight.detach().numpy().copy(), m.bias.detach().numpy().copy()) for m in mods]
+
+
+def gen_decoder():
+    """The reference's own decoder classes and GumbelMod on a small node sequence (the structure - trunk, two
+    heads, where ReLU and Identity apply, the heaviside gate - is what the oracle has to match)."""
+    from models.networks.basicCoders import BasicDecoder, BasicDecoderV3
+    from utils.dists.gumbelmod import GumbelMod
+    torch.manual_seed(32)
+    rng = np.random.default_rng(77)
+    B, seed = 24, 0x5EED + 9
+    # --- two-headed calorimeter decoder: latent 2n + 1 -> trunk -> (hits, activations)
+    nodes = [(33, 40), (40, 56), (56, 72), (72, 100)]
+    d3 = BasicDecoderV3(node_sequence=nodes, activation_fct=torch.nn.ReLU(), cfg=None)
+    states = (rng.random((B, 32)) < 0.5).astype(np.float32)
+    true_e = (rng.random((B, 1)) * 100).astype(np.float32)
+    x = np.concatenate([states, true_e], axis=1)
+    with torch.no_grad():
+        hits, act = d3(torch.from_numpy(x))
+    u = dec.hit_uniforms(seed, B, 100)
+    rho = (1.0 - u).astype(np.float32)
+    with RandInterposer(lambda i, s_: torch.from_numpy(rho)) as ri, torch.no_grad():
+        gate = GumbelMod()(hits, torch.tensor(7.0), False)
+        sample = torch.relu(act) * gate                              # gumboltCaloV5.py:93
+    assert ri.calls == 1
+    trunk, hh, ha = _layer_arrays(d3._layers), _layer_arrays(d3._layers2), _layer_arrays(d3._layers3)
+    oh, oa = dec.decoder_v3(trunk, hh, ha, x)
+    np.testing.assert_allclose(oh, hits.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(oa, act.numpy(), rtol=1e-5, atol=1e-5)
+    assert np.array_equal(dec.shower_tail(hits.numpy(), act.numpy(), rho), sample.numpy())
+    so, clean = dec.shower_philox(hits.numpy(), act.numpy(), seed)
+    assert clean.mean() > 0.99 and np.array_equal(so[clean], sample.numpy()[clean])
+    flat = {}
+    for name, ch in (("trunk", trunk), ("hits", hh), ("act", ha)):
+        for i, (W, b) in enumerate(ch):
+            flat["%s_W%d" % (name, i)] = W; flat["%s_b%d" % (name, i)] = b
+    np.savez_compressed(os.path.join(OUT, "decoder_v3.npz"), x=x, out_hits=hits.numpy(), out_act=act.numpy(), rho=rho,
+                        sample=sample.numpy(), seed=seed, n_trunk=len(trunk), n_head=len(hh), **flat)
+    print("decoder_v3: hit rate %.3f, clean %.4f" % (gate.numpy().mean(), clean.mean()))
+    # --- single-chain decoder (GumBolt / DiVAE MNIST-shape models)
+    nodes = [(16, 24), (24, 40), (40, 50)]
+    d1 = BasicDecoder(node_sequence=nodes, activation_fct=torch.nn.ReLU(), output_activation_fct=torch.nn.Identity(), cfg=None)
+    x1 = rng.standard_normal((B, 16)).astype(np.float32)
+    with torch.no_grad():
+        y1 = d1(torch.from_numpy(x1)).numpy()
+    layers = _layer_arrays(d1._layers)
+    np.testing.assert_allclose(dec.decoder_basic(layers, x1), y1, rtol=1e-5, atol=1e-5)
+    flat = {}
+    for i, (W, b) in enumerate(layers):
+        flat["W%d" % i] = W; flat["b%d" % i] = b
+    np.savez_compressed(os.path.join(OUT, "decoder_basic.npz"), x=x1, y=y1, n_layers=len(layers), **flat)
+    print("decoder_basic ok")
+
+
 def main():
     _ref_shim.install()
     os.makedirs(OUT, exist_ok=True)
@@ -231,6 +289,7 @@ def main():
     gen_cd1()
     gen_negphase()
     gen_port_check()
+    gen_decoder()
 
 
 if __name__ == "__main__":

@@ -33,6 +33,7 @@ TAG_GIBBS = 0      # Bernoulli draws of Gibbs half-steps
 TAG_INIT = 1       # chain (re-)initialisation, p = 1/2 (pcd.py:16-17)
 TAG_AIS = 2        # AIS transition draws
 TAG_AIS_INIT = 3   # AIS base-rate initial state
+TAG_HITS = 4       # hit gate of the shower decoder (oracle/decoder_oracle.py)
 TAG_EXTRA_BIT = 0x100  # OR-ed into the tag for the 16 refinement bits
 
 

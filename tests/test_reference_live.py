@@ -75,3 +75,34 @@ def test_reference_gumbolt_builds_on_top_of_the_dropin_classes():
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_decoder_oracle_matches_reference_at_the_calorimeter_shape():
+    """gumboltcaloV.yaml shape: latent 2*64+1 -> 200 -> 300 -> [400 -> 504] x 2 heads (gumboltCaloV5.py:100-103)."""
+    import torch
+    from oracle import decoder_oracle as dec, gen_golden
+    _ref_shim.install()
+    from models.networks.basicCoders import BasicDecoderV3
+    torch.manual_seed(3)
+    nodes = [(129, 200), (200, 300), (300, 400), (400, 504)]
+    d3 = BasicDecoderV3(node_sequence=nodes, activation_fct=torch.nn.ReLU(), cfg=None)
+    rng = np.random.default_rng(5)
+    x = np.concatenate([(rng.random((40, 128)) < 0.5).astype(np.float32), (rng.random((40, 1)) * 100).astype(np.float32)], 1)
+    with torch.no_grad():
+        hits, act = d3(torch.from_numpy(x))
+    la = gen_golden._layer_arrays
+    oh, oa = dec.decoder_v3(la(d3._layers), la(d3._layers2), la(d3._layers3), x)
+    np.testing.assert_allclose(oh, hits.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(oa, act.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_decoder_fixture_regenerates_identically(golden, tmp_path, monkeypatch):
+    from oracle import gen_golden
+    _ref_shim.install()
+    monkeypatch.setattr(gen_golden, "OUT", str(tmp_path))
+    gen_golden.gen_decoder()
+    for name in ("decoder_v3", "decoder_basic"):
+        new, old = dict(np.load(tmp_path / (name + ".npz"))), golden(name)
+        assert sorted(new) == sorted(old)
+        for key in new:
+            assert np.array_equal(new[key], old[key]), (name, key)
