@@ -330,13 +330,13 @@ size_t rbm_b200_decoder_workspace(const rbm_b200_decoder* d, int64_t B) {
 }
 
 int rbm_b200_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, float* out_hits, float* out_act,
-                             float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+                             float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, int params_staged,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   RBM_REQUIRE(d != nullptr, RBM_B200_ERR_INVALID, "decoder description is NULL");
   RBM_REQUIRE(B >= 0, RBM_B200_ERR_INVALID, "negative batch");
   int rc = require_device();
   if (rc) return rc;
-  return umma_decoder_forward(d, x, B, out_hits, out_act, samples, seed, chain_offset, step, workspace,
+  return umma_decoder_forward(d, x, B, out_hits, out_act, samples, seed, chain_offset, step, params_staged, workspace,
                               workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -1454,9 +1454,10 @@ int make_decoder_plan(const rbm_b200_decoder* d, int64_t B, DecoderPlan* out) {
       lp.lin = &l;
       lp.Kp = round_up(l.in_features, 64); lp.Np = round_up(l.out_features, 64);
       lp.bn = pick_block_n(lp.Np, pl.rows_pad);
+      // staged parameters first: their offsets do not depend on B, so a caller may keep them across calls
       lp.off_W = o; o = align(o + (size_t)lp.Np * 3 * lp.Kp * 2);
       lp.off_bias = o; o = align(o + (size_t)round_up(lp.Np, 256) * 4);
-      lp.off_out = o; o = align(o + (size_t)pl.rows_pad * 2 * lp.Np * 2);
+      lp.off_out = 0;
       dst.push_back(lp);
       prev = l.out_features;
     }
@@ -1475,9 +1476,12 @@ int make_decoder_plan(const rbm_b200_decoder* d, int64_t B, DecoderPlan* out) {
   }
   pl.Np_out = round_up(pl.n_out, 64);
   const int K0p = round_up(d->trunk[0].in_features, 64);
+  pl.off_nbias_hits = o; o = align(o + (size_t)round_up(pl.Np_out, 256) * 4);
+  // activations ([rows_pad, 2 Np] bf16 per hidden layer), input tile, hit gate
+  for (std::vector<LayerPlan>* ch : {&pl.trunk, &pl.hits, &pl.act})
+    for (LayerPlan& lp : *ch) { lp.off_out = o; o = align(o + (size_t)pl.rows_pad * 2 * lp.Np * 2); }
   pl.off_in = o; o = align(o + (size_t)pl.rows_pad * 2 * K0p * 2);
   pl.off_mask = o; o = align(o + (size_t)pl.rows_pad * pl.Np_out * 2);
-  pl.off_nbias_hits = o; o = align(o + (size_t)round_up(pl.Np_out, 256) * 4);
   pl.total = o + 1024;
   return 0;
 }
@@ -1498,8 +1502,8 @@ size_t umma_decoder_workspace_bytes(const rbm_b200_decoder* d, int64_t B) {
 }
 
 int umma_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, float* out_hits, float* out_act,
-                         float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, void* ws,
-                         size_t ws_bytes, cudaStream_t st) {
+                         float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, int params_staged,
+                         void* ws, size_t ws_bytes, cudaStream_t st) {
   DecoderPlan pl;
   int rc = make_decoder_plan(d, B, &pl);
   if (rc) return rc;
@@ -1536,8 +1540,8 @@ int umma_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, f
                                                            lp.lin->out_features, np256, 1.f);
     }
   };
-  stage_chain(pl.trunk); stage_chain(pl.hits); stage_chain(pl.act);
-  if (samples != nullptr) {
+  if (!params_staged) { stage_chain(pl.trunk); stage_chain(pl.hits); stage_chain(pl.act); }
+  if (!params_staged && !pl.hits.empty()) {
     const LayerPlan& lp = pl.hits.back();
     const int np256 = round_up(lp.Np, 256);
     pad_bias_kernel<<<ceil_div(np256, 256), 256, 0, st>>>(lp.lin->bias, nbias_hits, lp.lin->out_features, np256,

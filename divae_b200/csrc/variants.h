@@ -51,8 +51,8 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
 // decoder MLP on generated samples: one tcgen05 GEMM per layer, split-bf16 operands
 size_t umma_decoder_workspace_bytes(const rbm_b200_decoder* d, int64_t B);
 int umma_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, float* out_hits, float* out_act,
-                         float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, void* ws,
-                         size_t ws_bytes, cudaStream_t st);
+                         float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, int params_staged,
+                         void* ws, size_t ws_bytes, cudaStream_t st);
 
 size_t umma_ais_workspace_bytes(int nV, int nH, int64_t M);
 int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n_betas, uint64_t seed,

@@ -54,13 +54,23 @@ class DecoderRunner:
         self.in_features = self._trunk[0].in_features
         self.out_features = (self._act[-1] if self._act else self._trunk[-1]).out_features
         self.two_heads = bool(self._act)
+        self._desc = self._desc_key = self._keep = None
+        self._ws = self._ws_key = None
+
+    def _params(self):
+        return [t for m in self._trunk + self._hits + self._act for t in (m.weight, m.bias)]
 
     def _describe(self):
+        """(rbm_b200_decoder, key): ctypes description of the current parameters, rebuilt only when a parameter
+        tensor was replaced, moved or modified in place (an optimiser step bumps `_version`)."""
+        key = tuple((id(t), t._version, t.data_ptr()) for t in self._params())
+        if key == self._desc_key:
+            return self._desc, key
         keep = []
 
         def arr(mods):
             if not mods:
-                return None
+                return ctypes.cast(None, ctypes.POINTER(_lib.Linear))
             a = (_lib.Linear * len(mods))()
             for i, m in enumerate(mods):
                 w = _ops._f32c(m.weight.detach(), "decoder weight")
@@ -70,11 +80,9 @@ class DecoderRunner:
             keep.append(a)
             return a
 
-        t, h, a = arr(self._trunk), arr(self._hits), arr(self._act)
-        d = _lib.Decoder(len(self._trunk), len(self._act), t,
-                         h if h is not None else ctypes.cast(None, ctypes.POINTER(_lib.Linear)),
-                         a if a is not None else ctypes.cast(None, ctypes.POINTER(_lib.Linear)))
-        return d, keep
+        d = _lib.Decoder(len(self._trunk), len(self._act), arr(self._trunk), arr(self._hits), arr(self._act))
+        self._desc, self._desc_key, self._keep = d, key, keep
+        return d, key
 
     def _run(self, x, want_hits, want_act, want_samples, seed=0, chain_offset=0, step=0):
         lib = _lib.load()
@@ -82,7 +90,7 @@ class DecoderRunner:
         if x.dim() != 2 or x.shape[1] != self.in_features:
             raise RuntimeError("size mismatch: decoder expects [B, %d], got %s" % (self.in_features, tuple(x.shape)))
         B = x.shape[0]
-        d, keep = self._describe()
+        d, key = self._describe()
         dev = x.device
         new = lambda: torch.empty((B, self.out_features), dtype=torch.float32, device=dev)
         hits = new() if want_hits else None
@@ -92,11 +100,17 @@ class DecoderRunner:
             n = lib.rbm_b200_decoder_workspace(ctypes.byref(d), B)
             if n == 0 and B > 0:
                 _lib.check(-1, "decoder_workspace")
-            ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+            # the workspace (and the split parameters staged at its start) is kept across calls
+            staged = 0
+            if self._ws is not None and self._ws.device == dev and self._ws.numel() >= n:
+                staged = 1 if self._ws_key == key else 0
+            else:
+                self._ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
             _lib.check(lib.rbm_b200_decoder_forward(ctypes.byref(d), _ops._ptr(x), B, _ops._ptr(hits), _ops._ptr(act),
-                                                    _ops._ptr(samples), seed, chain_offset, step, _ops._ptr(ws), n,
-                                                    _ops._stream()), "decoder_forward")
-        del keep
+                                                    _ops._ptr(samples), seed, chain_offset, step, staged,
+                                                    _ops._ptr(self._ws), self._ws.numel(), _ops._stream()),
+                       "decoder_forward")
+            self._ws_key = key if B > 0 else self._ws_key
         return hits, act, samples
 
     def forward(self, x):
@@ -129,6 +143,10 @@ def generate_samples(model, num_samples=64, true_energy=None, seed=0):
         true_e = torch.rand((n, 1), device=v.device) * 100.
     else:
         true_e = torch.ones((n, 1), device=v.device) * true_energy
-    runner = DecoderRunner(model.decoder)
+    # one runner per model: it keeps the split parameters staged on the device between calls
+    runner = getattr(model, "_b200_decoder_runner", None)
+    if runner is None or runner._decoder is not model.decoder:
+        runner = DecoderRunner(model.decoder)
+        object.__setattr__(model, "_b200_decoder_runner", runner)
     x = torch.cat([v, h, true_e], dim=1)
     return true_e, runner.shower(x, seed=seed)

@@ -237,11 +237,17 @@ typedef struct rbm_b200_decoder {
  *            contract: key seed, counter (unit block of the output unit, chain_offset + row, step, tag 4).
  * Every layer is one tcgen05 GEMM (bf16 operands split in high + low parts, three products, fp32
  * accumulation: relative error ~2^-16 against the fp32 reference).  Needs an sm_100 device.
- * workspace: rbm_b200_decoder_workspace(...) bytes (0 for an invalid description). */
+ * workspace: rbm_b200_decoder_workspace(...) bytes (0 for an invalid description).  The staged (split,
+ * padded) parameters sit at the start of the workspace at offsets that do not depend on B:
+ *   params_staged = 0  stage them from the fp32 parameters (always correct);
+ *   params_staged = 1  the caller guarantees that this workspace was last used by a params_staged = 0
+ *                      call with the same description and that the parameters have not changed since
+ *                      (generation loops: saves 2 small launches per layer). */
 RBM_B200_API size_t rbm_b200_decoder_workspace(const rbm_b200_decoder *d, int64_t B);
 RBM_B200_API int rbm_b200_decoder_forward(const rbm_b200_decoder *d, const float *x, int64_t B, float *out_hits,
                                           float *out_act, float *samples, uint64_t seed, uint64_t chain_offset,
-                                          uint64_t step, void *workspace, size_t workspace_bytes, void *stream);
+                                          uint64_t step, int params_staged, void *workspace,
+                                          size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -183,3 +183,24 @@ def test_errors_are_loud():
         DecoderRunner(m)
     with pytest.raises(RuntimeError, match="two-headed"):
         DecoderRunner(Basic([(8, 8)]).to(DEV)).shower(torch.zeros(4, 8, device=DEV), seed=1)
+
+
+def test_staged_parameters_are_reused_and_refreshed():
+    """The runner keeps the split parameters in its workspace (params_staged = 1) until a parameter changes."""
+    torch.manual_seed(6)
+    m = V3([(33, 40), (40, 56), (56, 72), (72, 100)]).to(DEV)
+    r = DecoderRunner(m)
+    x = torch.randn(300, 33, device=DEV)
+    a1 = r.shower(x, seed=5)
+    a2 = r.shower(x, seed=5)                       # second call: staged parameters
+    assert torch.equal(a1, a2)
+    h1, c1 = r(x[:100])                            # smaller batch, same workspace, still staged
+    h2, c2 = DecoderRunner(m)(x[:100])
+    assert torch.equal(h1, h2) and torch.equal(c1, c2)
+    with torch.no_grad():
+        m._layers[0].weight.mul_(1.5)              # in-place update bumps _version -> restaged
+    b1 = r.shower(x, seed=5)
+    assert not torch.equal(a1, b1)
+    assert torch.equal(b1, DecoderRunner(m).shower(x, seed=5))
+    big = r.shower(torch.randn(5000, 33, device=DEV), seed=5)   # larger batch: new workspace, restaged
+    assert big.shape == (5000, 100)
