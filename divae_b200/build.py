@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librbm_b200.so")
 STAMP = os.path.join(HERE, ".librbm_b200.stamp")
-SOURCES = ["abi.cu", "gibbs_general.cu", "gibbs_smem.cu", "gibbs_umma.cu"]
+SOURCES = ["abi.cu", "gibbs_general.cu", "gibbs_smem.cu", "gibbs_umma.cu", "umma_decoder.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -1,0 +1,252 @@
+// ===================================================================================================
+// Decoder MLP on generated prior samples: the step right after the sampler in
+// shower / image generation (models/autoencoders/gumboltCaloV5.py:78-96, dvaepp.py:214-225) -
+//   BasicDecoder   (models/networks/basicCoders.py:28-42): chain of nn.Linear, ReLU between, last layer linear
+//   BasicDecoderV3 (basicCoders.py:63-84): shared trunk (_layers, all ReLU), two heads (_layers2 hits, _layers3
+//                  activations), last head layer linear
+//   shower tail    sample = relu(activations) * heaviside(hits + logit(rho)) (gumboltCaloV5.py:91-93,
+//                  utils/dists/gumbelmod.py:18-24) = relu(activations) * [sigmoid(hits) >= u], u = 1 - rho
+// Every layer is one launch of the SAME tcgen05 kernel as a Gibbs half-step (A = activations K-major, B = the
+// nn.Linear weight [out, in], which already is K-major).  fp32-grade accuracy on bf16 tensor cores: activations
+// and weights are split x = x_hi + x_lo (both bf16) and the GEMM runs over the tripled K axis
+//   [x_hi | x_hi | x_lo] . [W_hi | W_lo | W_hi]^T = x_hi W_hi + x_hi W_lo + x_lo W_hi      (error ~2^-16 relative),
+// accumulated in fp32 in TMEM.  Hidden layers store [high | low] bf16 tiles for the next layer (EPI_LINEAR_SPLIT),
+// the hits head ends in the Gibbs epilogue itself (sigmoid + Philox + compare, TAG_HITS) and the activation head
+// multiplies that gate into relu(acc + bias) on its way to the fp32 output (EPI_LINEAR_F32).
+#include <initializer_list>
+#include <vector>
+
+#include "umma_common.cuh"
+
+namespace rbm {
+namespace {
+
+constexpr uint32_t TAG_HITS = 4;   // Philox tag of the hit draws (oracle/philox.py)
+
+__global__ void split_input_kernel(const float* __restrict__ x, int64_t B, int n, uint16_t* __restrict__ dst,
+                                   int64_t rows_pad, int Kp) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_pad * Kp) return;
+  const int64_t r = idx / Kp;
+  const int c = (int)(idx % Kp);
+  const float val = (r < B && c < n) ? x[r * n + c] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
+  dst[r * (2 * (int64_t)Kp) + c] = __bfloat16_as_ushort(hi);
+  dst[r * (2 * (int64_t)Kp) + Kp + c] = __bfloat16_as_ushort(lo);
+}
+// W [N, K] fp32 -> [Np, 3 Kp] bf16 = [W_hi | W_lo | W_hi], zero padded
+__global__ void split_weight_kernel(const float* __restrict__ W, int N, int K, uint16_t* __restrict__ dst, int Np, int Kp) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Np * Kp) return;
+  const int r = (int)(idx / Kp), c = (int)(idx % Kp);
+  const float val = (r < N && c < K) ? W[(int64_t)r * K + c] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
+  uint16_t* row = dst + (int64_t)r * (3 * Kp);
+  row[c] = __bfloat16_as_ushort(hi);
+  row[Kp + c] = __bfloat16_as_ushort(lo);
+  row[2 * Kp + c] = __bfloat16_as_ushort(hi);
+}
+__global__ void pad_bias_kernel(const float* __restrict__ bias, float* __restrict__ dst, int n, int n_pad, float mul) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) dst[i] = i < n ? mul * bias[i] : 0.f;
+}
+
+struct LayerPlan {
+  const rbm_b200_linear* lin;
+  int Kp, Np, bn;
+  size_t off_W, off_bias, off_out;   // off_out: [rows_pad, 2 Np] bf16 (hidden layers)
+};
+struct DecoderPlan {
+  std::vector<LayerPlan> trunk, hits, act;
+  int64_t rows_pad;
+  int n_out, Np_out;
+  size_t off_in, off_mask, off_nbias_hits, total;
+};
+
+int make_decoder_plan(const rbm_b200_decoder* d, int64_t B, DecoderPlan* out) {
+  RBM_REQUIRE(d != nullptr && d->n_trunk >= 1 && d->trunk != nullptr, RBM_B200_ERR_INVALID, "decoder needs at least one trunk layer");
+  RBM_REQUIRE(d->n_head >= 0 && (d->n_head == 0 || d->head_act != nullptr), RBM_B200_ERR_INVALID, "decoder head description is incomplete");
+  DecoderPlan& pl = *out;
+  pl.rows_pad = ceil_div64(std::max<int64_t>(B, 1), 2 * BLOCK_M) * (2 * BLOCK_M);
+  auto align = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  size_t o = 0;
+  auto add_chain = [&](const rbm_b200_linear* ls, int n, int in_features, std::vector<LayerPlan>& dst) -> int {
+    int prev = in_features;
+    for (int i = 0; i < n; ++i) {
+      const rbm_b200_linear& l = ls[i];
+      RBM_REQUIRE(l.in_features >= 1 && l.out_features >= 1 && l.in_features <= 16384 && l.out_features <= 16384,
+                  RBM_B200_ERR_INVALID, "layer shape %d -> %d out of range", l.in_features, l.out_features);
+      RBM_REQUIRE(l.in_features == prev, RBM_B200_ERR_INVALID, "size mismatch: layer expects %d inputs, previous layer has %d",
+                  l.in_features, prev);
+      RBM_REQUIRE(l.weight != nullptr && l.bias != nullptr, RBM_B200_ERR_INVALID, "layer parameter pointer is NULL");
+      LayerPlan lp;
+      lp.lin = &l;
+      lp.Kp = round_up(l.in_features, 64); lp.Np = round_up(l.out_features, 64);
+      lp.bn = pick_block_n(lp.Np, pl.rows_pad);
+      // staged parameters first: their offsets do not depend on B, so a caller may keep them across calls
+      lp.off_W = o; o = align(o + (size_t)lp.Np * 3 * lp.Kp * 2);
+      lp.off_bias = o; o = align(o + (size_t)round_up(lp.Np, 256) * 4);
+      lp.off_out = 0;
+      dst.push_back(lp);
+      prev = l.out_features;
+    }
+    return 0;
+  };
+  int rc = add_chain(d->trunk, d->n_trunk, d->trunk[0].in_features, pl.trunk);
+  if (rc) return rc;
+  const int trunk_out = d->trunk[d->n_trunk - 1].out_features;
+  pl.n_out = trunk_out;
+  if (d->n_head > 0) {
+    if (d->head_hits && (rc = add_chain(d->head_hits, d->n_head, trunk_out, pl.hits))) return rc;
+    if ((rc = add_chain(d->head_act, d->n_head, trunk_out, pl.act))) return rc;
+    pl.n_out = d->head_act[d->n_head - 1].out_features;
+    RBM_REQUIRE(!d->head_hits || d->head_hits[d->n_head - 1].out_features == pl.n_out, RBM_B200_ERR_INVALID,
+                "size mismatch: the two heads end in %d and %d units", d->head_hits[d->n_head - 1].out_features, pl.n_out);
+  }
+  pl.Np_out = round_up(pl.n_out, 64);
+  const int K0p = round_up(d->trunk[0].in_features, 64);
+  pl.off_nbias_hits = o; o = align(o + (size_t)round_up(pl.Np_out, 256) * 4);
+  // activations ([rows_pad, 2 Np] bf16 per hidden layer), input tile, hit gate
+  for (std::vector<LayerPlan>* ch : {&pl.trunk, &pl.hits, &pl.act})
+    for (LayerPlan& lp : *ch) { lp.off_out = o; o = align(o + (size_t)pl.rows_pad * 2 * lp.Np * 2); }
+  pl.off_in = o; o = align(o + (size_t)pl.rows_pad * 2 * K0p * 2);
+  pl.off_mask = o; o = align(o + (size_t)pl.rows_pad * pl.Np_out * 2);
+  pl.total = o + 1024;
+  return 0;
+}
+
+template <int EPI>
+int launch_linear(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HalfStepArgs& a,
+                  int sm_count, cudaStream_t st) {
+  return bn == 256 ? launch_half_step_impl<256, false, EPI, 1, true>(ta, tb, to, a, sm_count, st)
+                   : launch_half_step_impl<128, false, EPI, 1, true>(ta, tb, to, a, sm_count, st);
+}
+
+}  // namespace
+
+size_t umma_decoder_workspace_bytes(const rbm_b200_decoder* d, int64_t B) {
+  DecoderPlan pl;
+  if (make_decoder_plan(d, B, &pl)) return 0;
+  return pl.total;
+}
+
+int umma_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, float* out_hits, float* out_act,
+                         float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, int params_staged,
+                         void* ws, size_t ws_bytes, cudaStream_t st) {
+  DecoderPlan pl;
+  int rc = make_decoder_plan(d, B, &pl);
+  if (rc) return rc;
+  RBM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, RBM_B200_ERR_WORKSPACE,
+              "decoder needs %zu bytes of workspace, got %zu", pl.total, ws_bytes);
+  RBM_REQUIRE(samples == nullptr || !pl.hits.empty(), RBM_B200_ERR_INVALID,
+              "shower samples need both heads (hits and activations)");
+  RBM_REQUIRE(out_hits == nullptr || !pl.hits.empty(), RBM_B200_ERR_INVALID, "there is no hits head to output");
+  if (B == 0) return 0;
+  RBM_REQUIRE(x != nullptr, RBM_B200_ERR_INVALID, "input pointer is NULL");
+  DeviceInfo di;
+  if ((rc = get_device_info(&di))) return rc;
+  RBM_REQUIRE(di.cc_major == 10, RBM_B200_ERR_NO_DEVICE, "the decoder path needs an sm_100 device (got cc %d.x)", di.cc_major);
+  const int sm_count = di.sm_count;
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  const int in_features = d->trunk[0].in_features;
+  const int K0p = round_up(in_features, 64);
+  uint16_t* A0 = reinterpret_cast<uint16_t*>(base + pl.off_in);
+  uint16_t* mask = reinterpret_cast<uint16_t*>(base + pl.off_mask);
+  float* nbias_hits = reinterpret_cast<float*>(base + pl.off_nbias_hits);
+
+  // stage: split input, split weights, padded biases
+  {
+    const int64_t n = pl.rows_pad * K0p;
+    split_input_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, B, in_features, A0, pl.rows_pad, K0p);
+  }
+  auto stage_chain = [&](const std::vector<LayerPlan>& ch) {
+    for (const LayerPlan& lp : ch) {
+      const int64_t n = (int64_t)lp.Np * lp.Kp;
+      split_weight_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(lp.lin->weight, lp.lin->out_features, lp.lin->in_features,
+                                                                     reinterpret_cast<uint16_t*>(base + lp.off_W), lp.Np, lp.Kp);
+      const int np256 = round_up(lp.Np, 256);
+      pad_bias_kernel<<<ceil_div(np256, 256), 256, 0, st>>>(lp.lin->bias, reinterpret_cast<float*>(base + lp.off_bias),
+                                                           lp.lin->out_features, np256, 1.f);
+    }
+  };
+  if (!params_staged) { stage_chain(pl.trunk); stage_chain(pl.hits); stage_chain(pl.act); }
+  if (!params_staged && !pl.hits.empty()) {
+    const LayerPlan& lp = pl.hits.back();
+    const int np256 = round_up(lp.Np, 256);
+    pad_bias_kernel<<<ceil_div(np256, 256), 256, 0, st>>>(lp.lin->bias, nbias_hits, lp.lin->out_features, np256,
+                                                         -1.4426950408889634f);
+  }
+  if ((rc = check_launch("decoder staging kernels"))) return rc;
+
+  // one layer = one launch.  mode: 0 hidden (split bf16 out), 1 fp32 out, 2 hit gate (Gibbs epilogue), 3 gated shower
+  auto run_layer = [&](const LayerPlan& lp, const uint16_t* A, int Kp_in, int mode, float* dst_f32) -> int {
+    CUtensorMap ta, tb, to;
+    int r;
+    if ((r = make_tmap(&ta, A, (uint64_t)pl.rows_pad, (uint64_t)(2 * Kp_in), (uint64_t)(2 * Kp_in), BLOCK_M))) return r;
+    if ((r = make_tmap(&tb, base + lp.off_W, (uint64_t)lp.Np, (uint64_t)(3 * lp.Kp), (uint64_t)(3 * lp.Kp), (uint32_t)lp.bn))) return r;
+    HalfStepArgs a{};
+    a.nbias = reinterpret_cast<const float*>(base + lp.off_bias);
+    a.ldo = lp.Np; a.m_tiles = (int)(pl.rows_pad / BLOCK_M); a.n_tiles = ceil_div(lp.Np, lp.bn);
+    a.k_blocks = 3 * lp.Kp / BLOCK_K; a.n_valid = lp.lin->out_features; a.chain_offset = chain_offset;
+    a.rows_valid = B;
+    if (mode == 0) {
+      uint16_t* out = reinterpret_cast<uint16_t*>(base + lp.off_out);
+      if ((r = make_tmap(&to, out, (uint64_t)pl.rows_pad, (uint64_t)(2 * lp.Np), (uint64_t)(2 * lp.Np), 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+      a.relu = 1; a.lo_off = lp.Np;
+      return launch_linear<EPI_LINEAR_SPLIT>(lp.bn, ta, tb, to, a, sm_count, st);
+    }
+    if (mode == 2) {
+      if ((r = make_tmap(&to, mask, (uint64_t)pl.rows_pad, (uint64_t)lp.Np, (uint64_t)lp.Np, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+      a.nbias = nbias_hits;
+      a.ctx = make_draw_ctx(seed, step, TAG_HITS);
+      return launch_linear<EPI_GIBBS>(lp.bn, ta, tb, to, a, sm_count, st);
+    }
+    a.out_f32 = dst_f32; a.ld_out = lp.lin->out_features;
+    a.relu = mode == 3 ? 1 : 0;
+    a.mask = mode == 3 ? mask : nullptr; a.ld_mask = lp.Np;
+    return launch_linear<EPI_LINEAR_F32>(lp.bn, ta, tb, ta, a, sm_count, st);   // no TMA store: any valid map
+  };
+
+  // trunk
+  const uint16_t* cur = A0;
+  int cur_Kp = K0p;
+  const bool single = pl.act.empty();
+  for (size_t i = 0; i < pl.trunk.size(); ++i) {
+    const LayerPlan& lp = pl.trunk[i];
+    if (single && i + 1 == pl.trunk.size()) {
+      // BasicDecoder: the last layer is linear (output_activation_fct = Identity, basicCoders.py:38-39)
+      if (out_act != nullptr && (rc = run_layer(lp, cur, cur_Kp, 1, out_act))) return rc;
+      return 0;
+    }
+    if ((rc = run_layer(lp, cur, cur_Kp, 0, nullptr))) return rc;
+    cur = reinterpret_cast<const uint16_t*>(base + lp.off_out); cur_Kp = lp.Np;
+  }
+  // heads
+  auto run_head = [&](const std::vector<LayerPlan>& ch, const uint16_t** last_in, int* last_Kp) -> int {
+    const uint16_t* a_in = cur; int kp = cur_Kp;
+    for (size_t i = 0; i + 1 < ch.size(); ++i) {
+      int r = run_layer(ch[i], a_in, kp, 0, nullptr);
+      if (r) return r;
+      a_in = reinterpret_cast<const uint16_t*>(base + ch[i].off_out); kp = ch[i].Np;
+    }
+    *last_in = a_in; *last_Kp = kp;
+    return 0;
+  };
+  const uint16_t* in_hits = nullptr; const uint16_t* in_act = nullptr;
+  int kp_hits = 0, kp_act = 0;
+  if (!pl.hits.empty() && (out_hits != nullptr || samples != nullptr)) {
+    if ((rc = run_head(pl.hits, &in_hits, &kp_hits))) return rc;
+    if (out_hits != nullptr && (rc = run_layer(pl.hits.back(), in_hits, kp_hits, 1, out_hits))) return rc;
+    if (samples != nullptr && (rc = run_layer(pl.hits.back(), in_hits, kp_hits, 2, nullptr))) return rc;
+  }
+  if (out_act != nullptr || samples != nullptr) {
+    if ((rc = run_head(pl.act, &in_act, &kp_act))) return rc;
+    if (out_act != nullptr && (rc = run_layer(pl.act.back(), in_act, kp_act, 1, out_act))) return rc;
+    if (samples != nullptr && (rc = run_layer(pl.act.back(), in_act, kp_act, 3, samples))) return rc;
+  }
+  return 0;
+}
+
+}  // namespace rbm

@@ -213,7 +213,7 @@ typedef struct rbm_b200_linear {
 } rbm_b200_linear;
 
 /* A decoder: `n_trunk` shared layers, then zero or two heads of `n_head` layers each.  Hidden
- * activation ReLU (configs/model/*.yaml: activation_fct: relu), last layer of a chain linear.
+ * activation ReLU (activation_fct: relu in the configs/model yaml files), last layer of a chain linear.
  *   BasicDecoder   (models/networks/basicCoders.py:28-42):  n_head = 0, trunk = _layers
  *   BasicDecoderV3 (basicCoders.py:63-84): trunk = _layers (all ReLU), head_hits = _layers2,
  *                  head_act = _layers3
