@@ -221,6 +221,7 @@ struct HalfStepArgs {
   const uint16_t* mask;    // EPI_LINEAR_F32: optional {0,1} bf16 gate [rows, ld_mask] multiplied into the output
   int ld_mask;
   int64_t rows_valid;      // EPI_LINEAR_F32: rows >= rows_valid are padding and are not stored
+  int f32_tma;             // EPI_LINEAR_F32: tmap_out describes out_f32 ([32 rows x 16 fp32] boxes, SWIZZLE_64B): staged TMA stores
 };
 
 // Epilogue flavours
@@ -282,6 +283,7 @@ struct EpiParams {
   const uint16_t* mask;
   int ld_mask;
   int64_t rows_valid;
+  int f32_tma;
 };
 
 // Epilogue of ONE 128 x BLOCK_N tile for one warp: TMEM -> decisions -> swizzled smem box -> TMA store.
@@ -466,17 +468,35 @@ __device__ __forceinline__ void epilogue_tile_linear(const EpiParams& ep, const 
         }
       } else {
         const int cbase = col0 + 16 * hh;
-        if (row < ep.rows_valid && cbase < ep.n_valid) {
-          if (ep.mask != nullptr) {
-            const uint4* mp = reinterpret_cast<const uint4*>(ep.mask + row * ep.ld_mask + cbase);
-            const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        const bool in_range = row < ep.rows_valid && cbase < ep.n_valid;
+        if (in_range && ep.mask != nullptr) {
+          const uint4* mp = reinterpret_cast<const uint4*>(ep.mask + row * ep.ld_mask + cbase);
+          const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              y[j] *= __uint_as_float(mw[j >> 1] << 16);
-              y[j + 1] *= __uint_as_float(mw[j >> 1] & 0xFFFF0000u);
+          for (int j = 0; j < 16; j += 2) {
+            y[j] *= __uint_as_float(mw[j >> 1] << 16);
+            y[j + 1] *= __uint_as_float(mw[j >> 1] & 0xFFFF0000u);
+          }
+        }
+        if (ep.f32_tma) {
+          // [32 rows x 16 fp32] box: a row is 64 B, chunk c at c ^ ((lane >> 1) & 3) (SWIZZLE_64B), one TMA store;
+          // rows and columns beyond the real extent are clipped by the tensor map
+          if (cbase < ep.n_valid) {   // warp-uniform
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              st_shared_v4(stage_row + (((uint32_t)ch ^ sw) << 4), __float_as_uint(y[4 * ch]), __float_as_uint(y[4 * ch + 1]),
+                           __float_as_uint(y[4 * ch + 2]), __float_as_uint(y[4 * ch + 3]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(tmap_out, stage_warp, cbase, row_base);
+              tma_store_commit();
             }
           }
+        } else if (in_range) {
           float* dst = ep.out_f32 + row * ep.ld_out + cbase;
           if ((ep.ld_out & 3) == 0 && cbase + 16 <= ep.n_valid && (reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0) {
 #pragma unroll
@@ -675,7 +695,7 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       ep.scale = args.scale; ep.bmul = args.bmul; ep.ratio = args.ratio; ep.debug_mode = args.debug_mode;
       ep.kf_magic = args.kf_magic;
       ep.relu = args.relu; ep.lo_off = args.lo_off; ep.out_f32 = args.out_f32; ep.ld_out = args.ld_out;
-      ep.mask = args.mask; ep.ld_mask = args.ld_mask; ep.rows_valid = args.rows_valid;
+      ep.mask = args.mask; ep.ld_mask = args.ld_mask; ep.rows_valid = args.rows_valid; ep.f32_tma = args.f32_tma;
       auto wait_full = [&] { mbar_wait(tmem_full_bar(as), ((uint32_t)it >> 1) & 1u); };
       auto release = [&] {
         if (CTAS == 2) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(as), 0));   // the leader's barrier
@@ -741,6 +761,23 @@ int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RBM_REQUIRE(r == CUDA_SUCCESS, RBM_B200_ERR_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// fp32 row-major [rows, cols] with row pitch `ld` elements (ld * 4 bytes must be a multiple of 16)
+int make_tmap_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                  uint32_t box_cols, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn fn = nullptr;
+  int rc = get_encode_fn(&fn);
+  if (rc) return rc;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RBM_REQUIRE(r == CUDA_SUCCESS, RBM_B200_ERR_INVALID, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
   return 0;
 }
 

@@ -23,17 +23,27 @@ namespace {
 
 constexpr uint32_t TAG_HITS = 4;   // Philox tag of the hit draws (oracle/philox.py)
 
+// x [B, n] fp32 -> [rows_pad, 2 Kp] bf16 = [x_hi | x_lo], zero padded; eight units per thread, 16-byte stores
 __global__ void split_input_kernel(const float* __restrict__ x, int64_t B, int n, uint16_t* __restrict__ dst,
                                    int64_t rows_pad, int Kp) {
+  const int groups = Kp >> 3;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows_pad * Kp) return;
-  const int64_t r = idx / Kp;
-  const int c = (int)(idx % Kp);
-  const float val = (r < B && c < n) ? x[r * n + c] : 0.f;
-  const __nv_bfloat16 hi = __float2bfloat16_rn(val);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
-  dst[r * (2 * (int64_t)Kp) + c] = __bfloat16_as_ushort(hi);
-  dst[r * (2 * (int64_t)Kp) + Kp + c] = __bfloat16_as_ushort(lo);
+  if (idx >= rows_pad * groups) return;
+  const int64_t r = idx / groups;
+  const int c0 = (int)(idx % groups) * 8;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float val = (r < B && c < n) ? __ldg(x + r * n + c) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(val);
+    const __nv_bfloat16 l = __float2bfloat16_rn(val - __bfloat162float(h));
+    if (j & 1) { hi[j >> 1] |= (uint32_t)__bfloat16_as_ushort(h) << 16; lo[j >> 1] |= (uint32_t)__bfloat16_as_ushort(l) << 16; }
+    else { hi[j >> 1] = __bfloat16_as_ushort(h); lo[j >> 1] = __bfloat16_as_ushort(l); }
+  }
+  uint16_t* row = dst + r * (2 * (int64_t)Kp);
+  *reinterpret_cast<uint4*>(row + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(row + Kp + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 // W [N, K] fp32 -> [Np, 3 Kp] bf16 = [W_hi | W_lo | W_hi], zero padded
 __global__ void split_weight_kernel(const float* __restrict__ W, int N, int K, uint16_t* __restrict__ dst, int Np, int Kp) {
@@ -158,7 +168,7 @@ int umma_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, f
 
   // stage: split input, split weights, padded biases
   {
-    const int64_t n = pl.rows_pad * K0p;
+    const int64_t n = pl.rows_pad * (K0p / 8);
     split_input_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, B, in_features, A0, pl.rows_pad, K0p);
   }
   auto stage_chain = [&](const std::vector<LayerPlan>& ch) {
@@ -206,7 +216,16 @@ int umma_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, f
     a.out_f32 = dst_f32; a.ld_out = lp.lin->out_features;
     a.relu = mode == 3 ? 1 : 0;
     a.mask = mode == 3 ? mask : nullptr; a.ld_mask = lp.Np;
-    return launch_linear<EPI_LINEAR_F32>(lp.bn, ta, tb, ta, a, sm_count, st);   // no TMA store: any valid map
+    // fp32 output through staged TMA stores when the row pitch allows it (multiple of 16 bytes, aligned base);
+    // the tensor map carries the REAL extent [B, out_features], so padding rows / columns are clipped
+    a.f32_tma = (lp.lin->out_features % 4 == 0 && ((uintptr_t)dst_f32 & 15) == 0) ? 1 : 0;
+    if (a.f32_tma) {
+      if ((r = make_tmap_f32(&to, dst_f32, (uint64_t)B, (uint64_t)lp.lin->out_features, (uint64_t)lp.lin->out_features, 32, 16,
+                             CU_TENSOR_MAP_SWIZZLE_64B))) return r;
+    } else {
+      to = ta;   // no TMA store: any valid map
+    }
+    return launch_linear<EPI_LINEAR_F32>(lp.bn, ta, tb, to, a, sm_count, st);
   };
 
   // trunk
