@@ -8,6 +8,7 @@
 // They serve odd shapes (200x200, 784x128), real-valued inputs, injected uniforms and
 // small batches; the SMEM and UMMA variants are the fast paths for binary chains.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -519,8 +520,281 @@ __global__ void cd_bias_update_kernel(const float* __restrict__ x, const float* 
   }
 }
 
+
+// ------------------------------------------------------------------ CD-k in ONE launch (small batches)
+// The reference's CD-1 on MNIST-shape data (BASELINE config 1: 784 x 128, batch 128) is ~0.13 GFLOP: as separate
+// launches it is 3k + 4 dependent launch latencies with 16-CTA grids.  Here the whole update is one cooperative
+// kernel: every phase is cut into ~100-130 work items spread over the SMs, phases are separated by grid barriers
+//   P1  ph0 = sigma(v0 W + c), h0 = [ph0 >= u_0]                              (rbm_standalone.py:79-84)
+//   k x P2  pv = sigma(h W^T + a)      P3  ph = sigma(pv W + c) [, h = [ph >= u_s]]     (:66-73)
+//   P4  dW, W, da, a, dc, c, loss with the OLD parameters' statistics          (:86-120)
+// Same arithmetic as the multi-launch path (fp32 FMA accumulation, sigmoid_precise, the same draw contract).
+struct CdFusedArgs {
+  float *W, *a, *c, *dW, *da, *dc;
+  int nV, nH;
+  const float* v0;
+  int B, k;
+  float lr, momentum, weight_cost;
+  const float* uniforms;   // [k + 1, nH] rows broadcast over the batch, or NULL (Philox draws)
+  uint64_t seed, draw_offset;
+  float* loss;
+  float *ph0, *h0, *hcur, *ph, *pv;
+  unsigned int* barrier;   // zeroed before the launch; counts CTA arrivals over all grid barriers of the launch
+};
+
+constexpr int kCdThreads = 256;
+constexpr int kCdSmemFloats = 4 * 32 * 33;   // the largest phase (P4: four [32][33] tiles)
+
+// out[r, j] = sigma(sum_i in[r, i] W[i, j] + c[j]); item = 4 rows x 32 hidden units, the 8 warps split the visible units
+__device__ void cd_hidden_phase(const CdFusedArgs& A, const float* in, float* probs, float* sample, int draw_idx, float* sm) {
+  constexpr int RB = 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col_items = ceil_div(A.nH, 32);
+  const int n_items = ceil_div(A.B, RB) * col_items;
+  const int n_gran = ceil_div(A.nV, 32);
+  float (*red)[RB][32] = reinterpret_cast<float (*)[RB][32]>(sm);   // [8][RB][32]
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int r0 = (item / col_items) * RB, j = (item % col_items) * 32 + lane;
+    float acc[RB];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) acc[rb] = 0.f;
+    for (int g = warp; g < n_gran; g += 8) {
+      const int i0 = g * 32;
+      float x[RB];
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) {
+        const int r = r0 + rb;
+        x[rb] = (r < A.B && i0 + lane < A.nV) ? in[(int64_t)r * A.nV + i0 + lane] : 0.f;
+      }
+      // all 32 W loads of the granule are issued before the first FMA (one L2 round trip per granule)
+      float w[32];
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk)
+        w[kk] = (j < A.nH && i0 + kk < A.nV) ? A.W[(int64_t)(i0 + kk) * A.nH + j] : 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) {
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) acc[rb] = fmaf(__shfl_sync(0xffffffffu, x[rb], kk), w[kk], acc[rb]);
+      }
+    }
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb) red[warp][rb][lane] = acc[rb];
+    __syncthreads();
+    if (warp < RB) {
+      const int r = r0 + warp;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += red[w][warp][lane];
+      if (r < A.B && j < A.nH) {
+        const float xx = sum + A.c[j];
+        const float pr = sigmoid_precise(xx);
+        if (probs) probs[(int64_t)r * A.nH + j] = pr;
+        if (sample) {
+          bool one;
+          if (A.uniforms) {
+            one = pr >= A.uniforms[(int64_t)draw_idx * A.nH + j];
+          } else {
+            const DrawCtx ctx = make_draw_ctx(A.seed, A.draw_offset + (uint64_t)draw_idx, TAG_GIBBS);
+            const uint32_t blk = unit_block_of((uint32_t)j), slot = unit_slot_of((uint32_t)j);
+            const uint4 wd = draw_block(ctx, blk, (uint32_t)r);
+            one = bernoulli_from_preact(xx, field16(wd, slot), [&]() { return field16(draw_block_extra(ctx, blk, (uint32_t)r), slot); });
+          }
+          sample[(int64_t)r * A.nH + j] = one ? 1.f : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// pv[r, i] = sigma(sum_j h[r, j] W[i, j] + a[i]); item = 32 rows x 32 visible units, hidden units staged 64 at a time
+__device__ void cd_visible_phase(const CdFusedArgs& A, const float* hin, float* pv, float* sm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float (*hs)[33] = reinterpret_cast<float (*)[33]>(sm);             // [64][33]: hs[j][r]
+  float (*ws)[65] = reinterpret_cast<float (*)[65]>(sm + 64 * 33);   // [32][65]: ws[i][j]
+  const int col_items = ceil_div(A.nV, 32);
+  const int n_items = ceil_div(A.B, 32) * col_items;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int r0 = (item / col_items) * 32, i0 = (item % col_items) * 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j0 = 0; j0 < A.nH; j0 += 64) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const int idx = threadIdx.x + l * kCdThreads;
+        const int x = idx >> 6, jj = idx & 63;    // x: row (for hs) or unit (for ws)
+        const bool jok = j0 + jj < A.nH;
+        hs[jj][x] = (jok && r0 + x < A.B) ? hin[(int64_t)(r0 + x) * A.nH + j0 + jj] : 0.f;
+        ws[x][jj] = (jok && i0 + x < A.nV) ? A.W[(int64_t)(i0 + x) * A.nH + j0 + jj] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int jj = 0; jj < 64; ++jj) {
+        const float hv = hs[jj][lane];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = fmaf(hv, ws[warp * 4 + q][jj], acc[q]);
+      }
+      __syncthreads();
+    }
+    const int r = r0 + lane;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + warp * 4 + q;
+      if (r < A.B && i < A.nV) pv[(int64_t)r * A.nV + i] = sigmoid_precise(acc[q] + A.a[i]);
+    }
+  }
+}
+
+// P4: weights (32 x 32 tiles, batch staged 32 chains at a time), biases and the reconstruction error
+__device__ void cd_update_phase(const CdFusedArgs& A, float* sm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float (*v0s)[33] = reinterpret_cast<float (*)[33]>(sm);
+  float (*pvs)[33] = reinterpret_cast<float (*)[33]>(sm + 32 * 33);
+  float (*h0s)[33] = reinterpret_cast<float (*)[33]>(sm + 2 * 32 * 33);
+  float (*phs)[33] = reinterpret_cast<float (*)[33]>(sm + 3 * 32 * 33);
+  const int col_items = ceil_div(A.nH, 32);
+  const int n_items = ceil_div(A.nV, 32) * col_items;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int i0 = (item / col_items) * 32, j0 = (item % col_items) * 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // the tiles of the first tile column also own the visible-bias sums of their 32 units (warp 0), the tiles
+    // of the first tile row the hidden-bias sums of theirs (warp 1): the operands are already in shared memory
+    float bsum = 0.f, bsq = 0.f;
+    for (int b0 = 0; b0 < A.B; b0 += 32) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const int idx = threadIdx.x + l * kCdThreads;
+        const int b = idx >> 5, x = idx & 31;
+        const bool bok = b0 + b < A.B;
+        const bool iok = bok && i0 + x < A.nV, jok = bok && j0 + x < A.nH;
+        v0s[b][x] = iok ? A.v0[(int64_t)(b0 + b) * A.nV + i0 + x] : 0.f;
+        pvs[b][x] = iok ? A.pv[(int64_t)(b0 + b) * A.nV + i0 + x] : 0.f;
+        h0s[b][x] = jok ? A.h0[(int64_t)(b0 + b) * A.nH + j0 + x] : 0.f;
+        phs[b][x] = jok ? A.ph[(int64_t)(b0 + b) * A.nH + j0 + x] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int b = 0; b < 32; ++b) {
+        const float hj = h0s[b][lane], pj = phs[b][lane];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          acc[q] = fmaf(v0s[b][warp * 4 + q], hj, fmaf(-pvs[b][warp * 4 + q], pj, acc[q]));
+      }
+      if (j0 == 0 && warp == 0) {
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {
+          const float d = v0s[b][lane] - pvs[b][lane];   // zero padded outside the batch / the units
+          bsum += d;
+          bsq = fmaf(d, d, bsq);
+        }
+      }
+      if (i0 == 0 && warp == 1 && j0 + lane < A.nH) {
+        float p0[32];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) p0[b] = b0 + b < A.B ? A.ph0[(int64_t)(b0 + b) * A.nH + j0 + lane] : 0.f;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) bsum += p0[b] - phs[b][lane];
+      }
+      __syncthreads();
+    }
+    if (j0 == 0 && warp == 0) {
+      const int u = i0 + lane;
+      if (u < A.nV) {
+        const float up = A.da[u] * A.momentum + bsum;
+        A.da[u] = up;
+        A.a[u] += up * A.lr;
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) bsq += __shfl_xor_sync(0xffffffffu, bsq, off);
+      if (lane == 0 && bsq != 0.f) atomicAdd(A.loss, bsq);
+    }
+    if (i0 == 0 && warp == 1) {
+      const int u = j0 + lane;
+      if (u < A.nH) {
+        const float up = A.dc[u] * A.momentum + bsum;
+        A.dc[u] = up;
+        A.c[u] += up * A.lr;
+      }
+    }
+    const int j = j0 + lane;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + warp * 4 + q;
+      if (i < A.nV && j < A.nH) {
+        const int64_t idx = (int64_t)i * A.nH + j;
+        const float w = A.W[idx];
+        const float u = A.dW[idx] * A.momentum + acc[q] - w * A.weight_cost;
+        A.dW[idx] = u;
+        A.W[idx] = w + u * A.lr;
+      }
+    }
+  }
+}
+
+// Grid barrier number `n` (1, 2, ...) of this launch: every CTA adds one arrival to a counter that starts at zero
+// and waits until n * gridDim.x arrivals are in.  The launch is cooperative, so all CTAs are resident.  (The
+// cooperative-groups grid.sync() spent ~20 us per barrier here: its poll loop runs a gpu-scope fence with an L1
+// invalidation per iteration; an acquire load per iteration is enough.)
+__device__ __forceinline__ void cd_grid_barrier(unsigned int* counter, unsigned int n) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned int target = n * gridDim.x;
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kCdThreads)
+cd_fused_kernel(const CdFusedArgs A) {
+  __shared__ float sm[kCdSmemFloats];
+  unsigned int nbar = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *A.loss = 0.f;   // added to in P4, three grid barriers later
+  cd_hidden_phase(A, A.v0, A.ph0, A.h0, 0, sm);
+  cd_grid_barrier(A.barrier, ++nbar);
+  const float* hin = A.h0;
+  for (int s = 0; s < A.k; ++s) {
+    cd_visible_phase(A, hin, A.pv, sm);
+    cd_grid_barrier(A.barrier, ++nbar);
+    // the draw after the last sweep is discarded by the reference
+    cd_hidden_phase(A, A.pv, A.ph, s + 1 < A.k ? A.hcur : nullptr, s + 1, sm);
+    cd_grid_barrier(A.barrier, ++nbar);
+    hin = A.hcur;
+  }
+  cd_update_phase(A, sm);
+}
+
+// true if the fused kernel was launched
+int cd_step_fused(const CdFusedArgs& A, cudaStream_t st, bool* launched) {
+  *launched = false;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  // per device: 0 = not queried yet, 1 = usable, -1 = no cooperative launch / kernel does not fit
+  static int usable[64] = {0};
+  const int dev = di.device >= 0 && di.device < 64 ? di.device : 0;
+  if (usable[dev] == 0) {
+    int coop = 0, per_sm = 0;
+    RBM_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, di.device));
+    RBM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cd_fused_kernel, kCdThreads, 0));
+    usable[dev] = (coop && per_sm >= 1) ? 1 : -1;
+  }
+  if (usable[dev] < 0) return 0;
+  const int items = std::max({ceil_div(A.B, 4) * ceil_div(A.nH, 32), ceil_div(A.B, 32) * ceil_div(A.nV, 32),
+                              ceil_div(A.nV, 32) * ceil_div(A.nH, 32)});
+  const int grid = std::max(1, std::min(items, di.sm_count));
+  RBM_CUDA_TRY(cudaMemsetAsync(A.barrier, 0, sizeof(unsigned int), st));
+  void* params[] = {const_cast<CdFusedArgs*>(&A)};
+  RBM_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)cd_fused_kernel, dim3((unsigned)grid), dim3(kCdThreads), params, 0, st));
+  *launched = true;
+  return check_launch("cd_fused_kernel");
+}
+
 size_t general_cd_workspace(int nV, int nH, int64_t B) {
-  return sizeof(float) * (size_t)B * (size_t)(4 * nH + nV);
+  return sizeof(float) * (size_t)B * (size_t)(4 * nH + nV) + 256;   // + the fused kernel's grid-barrier counter
 }
 
 // One CD-k update (sandbox/rbm_standalone.py:75-121), 3k + 4 launches, everything in fp32.
@@ -532,9 +806,21 @@ int general_cd_step(float* W, float* a, float* c, float* dW, float* da, float* d
   float* hcur = h0 + (size_t)B * nH;
   float* ph = hcur + (size_t)B * nH;
   float* pv = ph + (size_t)B * nH;
+  int rc;
+  // small batches (the reference's CD-1 on 128 digits): one cooperative launch instead of 3k + 4 launches
+  static const int fused_mode = [] { const char* e = getenv("RBM_B200_CD_FUSED"); return e ? atoi(e) : -1; }();
+  if (fused_mode != 0 && B <= 1024) {
+    CdFusedArgs fa{};
+    fa.W = W; fa.a = a; fa.c = c; fa.dW = dW; fa.da = da; fa.dc = dc; fa.nV = nV; fa.nH = nH; fa.v0 = v0; fa.B = (int)B;
+    fa.k = k; fa.lr = lr; fa.momentum = momentum; fa.weight_cost = weight_cost; fa.uniforms = uniforms; fa.seed = seed;
+    fa.draw_offset = draw_offset; fa.loss = loss; fa.ph0 = ph0; fa.h0 = h0; fa.hcur = hcur; fa.ph = ph; fa.pv = pv;
+    fa.barrier = reinterpret_cast<unsigned int*>(pv + (size_t)B * nV);
+    bool launched = false;
+    if ((rc = cd_step_fused(fa, st, &launched))) return rc;
+    if (launched) return 0;
+  }
   rbm_b200_params p{};
   p.n_visible = nV; p.n_hidden = nH; p.W = W; p.vbias = a; p.hbias = c;
-  int rc;
   const int draw_mode = uniforms ? RBM_B200_MODE_INJECTED : RBM_B200_MODE_SAMPLE;
   auto u_row = [&](int i) { return uniforms ? uniforms + (size_t)i * nH : nullptr; };
   // positive phase: ph0 = sigma(v0 W + c);  h0 = (ph0 >= u_0)                              :79-84
