@@ -43,16 +43,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
-#ifdef RBM_TRYWAIT_HINT
-    // suspend-time hint: the thread may sleep in hardware up to this many ns before try_wait returns false
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity), "r"((uint32_t)RBM_TRYWAIT_HINT)
-        : "memory");
-#else
+    // (a suspend-time hint on try_wait changed nothing: profiles/r01_pairs_vs_single.txt)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -60,7 +51,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-#endif
   } while (!done);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -310,14 +300,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
         w[b][0] = x.x; w[b][1] = x.y; w[b][2] = x.z; w[b][3] = x.w;
       }
     };
-#ifndef RBM_LATE_PHILOX
     draw_group(0);
-#endif
     // all lanes poll: measured 8 % faster than one polling lane + __syncwarp (profiles/r01_pairs_vs_single.txt)
     wait_full();
-#ifdef RBM_LATE_PHILOX
-    draw_group(0);
-#endif
     tcgen05_fence_after();
 #pragma unroll 1
     for (int g = 0; g < kGroups; ++g) {
@@ -325,13 +310,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
       const int col0 = n_blk * BLOCK_N + col_in_tile;
       const bool live = col0 < ep.ldo;   // tile overhang beyond the padded unit count
       const uint32_t blk0 = (uint32_t)(col0 >> 5) * 4u;
-#ifndef RBM_DEBUG_NO_WAIT_READ
       if (live) {
         // the previous TMA store of this warp must have finished READING the staging box
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
       }
-#endif
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t r[16];
