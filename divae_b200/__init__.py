@@ -14,6 +14,6 @@ from .samplers.baseSampler import BaseSampler  # noqa: F401
 from .samplers.gibbsSampler import GibbsSampler  # noqa: F401
 from .samplers.pcd import PCD  # noqa: F401
 from ._ops import energy_exp  # noqa: F401
-from .decoder import DecoderRunner, generate_samples  # noqa: F401
+from .decoder import DecoderRunner, EncoderRunner, generate_samples  # noqa: F401
 
-__all__ = ["RBM", "BaseSampler", "GibbsSampler", "PCD", "energy_exp", "DecoderRunner", "generate_samples"]
+__all__ = ["RBM", "BaseSampler", "GibbsSampler", "PCD", "energy_exp", "DecoderRunner", "EncoderRunner", "generate_samples"]

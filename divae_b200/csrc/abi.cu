@@ -340,4 +340,14 @@ int rbm_b200_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t 
                               workspace_bytes, (cudaStream_t)stream);
 }
 
+int rbm_b200_gumbel_smooth(float* logits, float* samples, int64_t B, int32_t n, float beta, int is_training, int clamp,
+                           uint64_t seed, uint64_t chain_offset, uint64_t step, uint32_t unit_offset, void* stream) {
+  RBM_REQUIRE(B >= 0 && n >= 0, RBM_B200_ERR_INVALID, "negative shape");
+  RBM_REQUIRE((B == 0 || n == 0) || (logits && samples), RBM_B200_ERR_INVALID, "NULL pointer");
+  int rc = require_device();
+  if (rc) return rc;
+  return gumbel_smooth(logits, samples, B, n, beta, is_training, clamp, seed, chain_offset, step, unit_offset,
+                       (cudaStream_t)stream);
+}
+
 }  // extern "C"

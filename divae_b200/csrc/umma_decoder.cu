@@ -63,6 +63,40 @@ __global__ void pad_bias_kernel(const float* __restrict__ bias, float* __restric
   if (i < n_pad) dst[i] = i < n ? mul * bias[i] : 0.f;
 }
 
+// Gumbel smoothing / gate of posterior logits (hierarchical encoder side):
+//   l = clamp(logit, -88, 88)                                   models/networks/hierarchicalEncoder.py:167
+//   training: z = sigmoid((l + log(rho) - log(1 - rho)) * beta) utils/dists/gumbelmod.py:18-21
+//   else:     z = heaviside(l + log(rho) - log(1 - rho))        gumbelmod.py:22-23  = [sigmoid(l) >= u], u = 1 - rho
+// rho comes from the library's draw contract (unit = unit_offset + column, chain = chain_offset + row, tag 5):
+// u32 = u16 * 65536 + e16 (main and refinement fields), rho = 1 - (u32 + 0.5) / 2^32 in (0, 1).
+constexpr uint32_t TAG_SMOOTH = 5;
+
+__global__ void gumbel_smooth_kernel(float* __restrict__ logits, float* __restrict__ samples, int64_t B, int n, float beta,
+                                     int is_training, int clamp, DrawCtx ctx, uint64_t chain_offset, uint32_t unit_offset) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * n) return;
+  const int64_t r = idx / n;
+  const int cidx = (int)(idx % n);
+  float l = logits[idx];
+  if (clamp) {
+    l = fminf(fmaxf(l, -88.f), 88.f);
+    logits[idx] = l;
+  }
+  const uint32_t unit = unit_offset + (uint32_t)cidx;
+  const uint32_t chain = (uint32_t)(chain_offset + (uint64_t)r);
+  const uint32_t blk = unit_block_of(unit), slot = unit_slot_of(unit);
+  const uint32_t k16 = field16(draw_block(ctx, blk, chain), slot);
+  if (is_training) {
+    const uint32_t e16 = field16(draw_block_extra(ctx, blk, chain), slot);
+    const float u = ((float)(k16 * 65536u + e16) + 0.5f) * 2.3283064365386963e-10f;   // (u32 + 0.5) / 2^32, rounded to fp32
+    const float rho = fminf(fmaxf(1.0f - u, 5.9604645e-8f), 1.0f - 5.9604645e-8f);
+    samples[idx] = sigmoid_precise((l + logf(rho) - logf(1.0f - rho)) * beta);
+  } else {
+    const bool one = bernoulli_from_preact(l, k16, [&]() { return field16(draw_block_extra(ctx, blk, chain), slot); });
+    samples[idx] = one ? 1.f : 0.f;
+  }
+}
+
 struct LayerPlan {
   const rbm_b200_linear* lin;
   int Kp, Np, bn;
@@ -135,6 +169,15 @@ int launch_linear(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CU
 }
 
 }  // namespace
+
+int gumbel_smooth(float* logits, float* samples, int64_t B, int n, float beta, int is_training, int clamp, uint64_t seed,
+                  uint64_t chain_offset, uint64_t step, uint32_t unit_offset, cudaStream_t st) {
+  if (B == 0 || n == 0) return 0;
+  gumbel_smooth_kernel<<<(unsigned)ceil_div64(B * n, 256), 256, 0, st>>>(logits, samples, B, n, beta, is_training, clamp,
+                                                                        make_draw_ctx(seed, step, TAG_SMOOTH), chain_offset,
+                                                                        unit_offset);
+  return check_launch("gumbel_smooth_kernel");
+}
 
 size_t umma_decoder_workspace_bytes(const rbm_b200_decoder* d, int64_t B) {
   DecoderPlan pl;

@@ -54,6 +54,10 @@ int umma_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, f
                          float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, int params_staged,
                          void* ws, size_t ws_bytes, cudaStream_t st);
 
+// posterior side: clamp + Gumbel smoothing / gate of encoder logits, Philox draws
+int gumbel_smooth(float* logits, float* samples, int64_t B, int n, float beta, int is_training, int clamp, uint64_t seed,
+                  uint64_t chain_offset, uint64_t step, uint32_t unit_offset, cudaStream_t st);
+
 size_t umma_ais_workspace_bytes(int nV, int nH, int64_t M);
 int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n_betas, uint64_t seed,
                  uint64_t chain_offset, double* logw, void* ws, size_t ws_bytes, cudaStream_t st);

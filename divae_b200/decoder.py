@@ -129,6 +129,72 @@ class DecoderRunner:
         return self._run(x, False, False, True, seed, chain_offset, step)[2]
 
 
+class _Chain:
+    """Minimal BasicDecoder-shaped view of one hierarchy level's nn.Sequential for DecoderRunner."""
+
+    def __init__(self, linears):
+        self._layers = linears
+        self._activation_fct = torch.nn.ReLU()
+
+
+class EncoderRunner:
+    """Inference forward of the reference's HierarchicalEncoder with the Gumbel smoother
+    (models/networks/hierarchicalEncoder.py:139-183).
+
+    Per hierarchy level: logits = clamp(net(cat([x] + samples)), -88, 88) - the level's MLP through
+    rbm_b200_decoder_forward (tcgen05 GEMMs on split-bf16 operands) - and
+    samples = GumbelMod(logits, beta, is_training) through rbm_b200_gumbel_smooth (Philox draws).
+    Forward only: there is no backward pass, so training keeps the reference's torch encoder."""
+
+    def __init__(self, encoder, beta=None):
+        nets = getattr(encoder, "_networks", None)
+        if nets is None or len(nets) == 0:
+            raise RuntimeError("divae_b200 encoder: expected a HierarchicalEncoder with `_networks`")
+        smoother = getattr(encoder, "smoothing_dist_mod", None)
+        if smoother is not None and type(smoother).__name__ != "GumbelMod":
+            raise RuntimeError("divae_b200 encoder: only the Gumbel smoother (gumbelmod.py) is implemented, got %r" % (smoother,))
+        self._levels = []
+        for net in nets:
+            mods = list(net)
+            linears = [m for m in mods if isinstance(m, torch.nn.Linear)]
+            others = [m for m in mods if not isinstance(m, torch.nn.Linear)]
+            if not linears or any(not isinstance(m, (torch.nn.ReLU, torch.nn.Identity)) for m in others):
+                raise RuntimeError("divae_b200 encoder: levels must be Linear/ReLU stacks (hierarchicalEncoder.py:86-96)")
+            self._levels.append(DecoderRunner(_Chain(linears)))
+        if beta is None:
+            cfg = getattr(encoder, "_config", None)
+            beta = getattr(getattr(cfg, "model", None), "beta_smoothing_fct", None)
+        if beta is None:
+            raise RuntimeError("divae_b200 encoder: pass beta= (config.model.beta_smoothing_fct)")
+        self.beta = float(beta)
+        self.n_latent = self._levels[0].out_features
+
+    def forward(self, x, is_training=False, seed=0, chain_offset=0, step=0):
+        """Returns (beta, post_logits, post_samples) like HierarchicalEncoder.forward (hierarchicalEncoder.py:183)."""
+        lib = _lib.load()
+        scale = None
+        if isinstance(x, tuple):          # (data, per-sample factor): samples are multiplied by x[1] (hierarchicalEncoder.py:178-179)
+            x, scale = x
+        x = _ops._f32c(x, "encoder input")
+        B = x.shape[0]
+        post_logits, post_samples = [], []
+        with torch.no_grad(), _ops._on_device(x.device):
+            for lvl, runner in enumerate(self._levels):
+                inp = torch.cat([x] + post_samples, dim=1) if post_samples else x
+                logits = runner(inp)
+                samples = torch.empty_like(logits)
+                _lib.check(lib.rbm_b200_gumbel_smooth(_ops._ptr(logits), _ops._ptr(samples), B, logits.shape[1], self.beta,
+                                                      1 if is_training else 0, 1, seed, chain_offset, step,
+                                                      lvl * self.n_latent, _ops._stream()), "gumbel_smooth")
+                if scale is not None:
+                    samples = samples * _ops._f32c(scale, "scale").reshape(B, 1)
+                post_logits.append(logits); post_samples.append(samples)
+        beta = torch.tensor(self.beta, dtype=torch.float, device=x.device)
+        return beta, post_logits, post_samples
+
+    __call__ = forward
+
+
 def generate_samples(model, num_samples=64, true_energy=None, seed=0):
     """Drop-in for GumBoltCaloV5.generate_samples (models/autoencoders/gumboltCaloV5.py:78-96).
 

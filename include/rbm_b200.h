@@ -249,6 +249,21 @@ RBM_B200_API int rbm_b200_decoder_forward(const rbm_b200_decoder *d, const float
                                           uint64_t step, int params_staged, void *workspace,
                                           size_t workspace_bytes, void *stream);
 
+/* ---- next row: the posterior side, inference forward ----------------------------
+ * Clamp + Gumbel smoothing (training) or gate (evaluation) of one hierarchy level's logits, replacing
+ *   logits = torch.clamp(current_net(current_input), min=-88., max=88.)        hierarchicalEncoder.py:167
+ *   samples = self.smoothing_dist_mod(logits, beta, is_training)               hierarchicalEncoder.py:176
+ * with GumbelMod (utils/dists/gumbelmod.py:14-24): rho ~ U(0,1);
+ *   is_training: samples = sigmoid((logits + log(rho) - log(1-rho)) * beta)
+ *   else:        samples = heaviside(logits + log(rho) - log(1-rho), 0) = [sigmoid(logits) >= 1 - rho]
+ * The level's MLP itself runs through rbm_b200_decoder_forward (a chain with n_head = 0).
+ *   logits  [B, n] fp32, clamped IN PLACE when clamp != 0;   samples [B, n] fp32, overwritten.
+ *   rho = 1 - (u32 + 0.5) / 2^32 with u32 from the Philox contract: key seed, counter (unit block of
+ *   unit_offset + column, chain_offset + row, step, tag 5) - pass the level's first latent index as unit_offset. */
+RBM_B200_API int rbm_b200_gumbel_smooth(float *logits, float *samples, int64_t B, int32_t n, float beta,
+                                        int is_training, int clamp, uint64_t seed, uint64_t chain_offset,
+                                        uint64_t step, uint32_t unit_offset, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

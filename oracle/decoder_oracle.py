@@ -76,3 +76,72 @@ def shower_philox(output_hits, output_activations, seed, chain_offset=0, step=0,
     u = hit_uniforms(seed, p.shape[0], p.shape[1], chain_offset, step)
     gate = (p >= u).astype(F32)
     return relu(np.asarray(output_activations, dtype=F32)) * gate, np.abs(p - u) >= tol
+
+
+# ---------------------------------------------------------------- posterior side
+TAG_SMOOTH = 5   # Philox tag of the smoothing draws (csrc/umma_decoder.cu: TAG_SMOOTH)
+
+
+def smooth_u32(seed, n_rows, n, chain_offset=0, step=0, unit_offset=0):
+    """32-bit draws (u16 * 65536 + e16) of the device contract for units unit_offset .. unit_offset + n - 1."""
+    chains = np.arange(n_rows, dtype=np.uint64) + np.uint64(chain_offset)
+    c2, c3 = _step_words(step, TAG_SMOOTH)
+    u16 = philox.draw_u16(unit_offset + n, chains, c2, c3, seed)[:, unit_offset:].astype(np.uint64)
+    c2e, c3e = _step_words(step, TAG_SMOOTH | philox.TAG_EXTRA_BIT)
+    e16 = philox.draw_u16(unit_offset + n, chains, c2e, c3e, seed)[:, unit_offset:].astype(np.uint64)
+    return u16 * np.uint64(65536) + e16
+
+
+def smooth_rho(u32):
+    """rho of the device's training-mode smoothing, in its fp32 arithmetic: 1 - (float(u32) + 0.5) * 2^-32, clamped
+    to [2^-24, 1 - 2^-24]."""
+    u = (u32.astype(F32) + F32(0.5)) * F32(2.0 ** -32)
+    return np.clip(F32(1) - u, F32(2.0 ** -24), F32(1) - F32(2.0 ** -24)).astype(F32)
+
+
+def gumbel_mod(logits, beta, is_training, rho):
+    """GumbelMod.forward (utils/dists/gumbelmod.py:14-24) with an injected rho."""
+    logits = np.asarray(logits, dtype=F32); rho = np.asarray(rho, dtype=F32)
+    lg = (logits + np.log(rho) - np.log(F32(1) - rho)).astype(F32)
+    if is_training:
+        return sigmoid(lg * F32(beta))
+    return np.where(lg > 0, F32(1), F32(0))
+
+
+def encoder_forward(levels, x, beta, is_training, rho_of_level):
+    """HierarchicalEncoder.forward (models/networks/hierarchicalEncoder.py:139-183) for a tensor input:
+    per level  logits = clamp(net(cat([x] + samples)), -88, 88);  samples = GumbelMod(logits, beta, is_training).
+    levels = [[(W, b), ...], ...] (ReLU between the layers, last layer linear: hierarchicalEncoder.py:86-96);
+    rho_of_level(lvl, shape) supplies the uniforms.  Returns (post_logits, post_samples)."""
+    x = np.asarray(x, dtype=F32)
+    post_logits, post_samples = [], []
+    for lvl, chain in enumerate(levels):
+        inp = np.concatenate([x] + post_samples, axis=1)
+        logits = np.clip(chain_forward(chain, inp, last_linear=True), F32(-88), F32(88)).astype(F32)
+        post_logits.append(logits)
+        post_samples.append(gumbel_mod(logits, beta, is_training, rho_of_level(lvl, logits.shape)).astype(F32))
+    return post_logits, post_samples
+
+
+def encoder_forward_philox(levels, x, beta, is_training, seed, chain_offset=0, step=0, tol=1e-4):
+    """The same with the device's own draws (level l uses units l * n_latent ...).  Evaluation mode decides
+    [sigmoid(l) >= u] against the exact u = u32 / 2^32 like the device; `clean` marks the entries whose draw is at
+    least `tol` away from the threshold AT EVERY level that feeds them (a flipped bit changes later levels)."""
+    x = np.asarray(x, dtype=F32)
+    post_logits, post_samples = [], []
+    clean = np.ones(x.shape[0], dtype=bool)
+    off = 0
+    for chain in levels:
+        inp = np.concatenate([x] + post_samples, axis=1)
+        logits = np.clip(chain_forward(chain, inp, last_linear=True), F32(-88), F32(88)).astype(F32)
+        u32 = smooth_u32(seed, x.shape[0], logits.shape[1], chain_offset, step, off)
+        if is_training:
+            z = gumbel_mod(logits, beta, True, smooth_rho(u32))
+        else:
+            p = sigmoid(logits).astype(np.float64)
+            u = u32.astype(np.float64) / 4294967296.0
+            z = (p >= u).astype(F32)
+            clean &= (np.abs(p - u) >= tol).all(axis=1)
+        post_logits.append(logits); post_samples.append(z.astype(F32))
+        off += logits.shape[1]
+    return post_logits, post_samples, clean

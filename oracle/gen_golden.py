@@ -17,6 +17,8 @@ Fixtures (all small):
   decoder_v3.npz   BasicDecoderV3.forward + the shower tail of generate_samples with GumbelMod
                    (basicCoders.py:63-84, gumboltCaloV5.py:88-93, gumbelmod.py:18-24)
   decoder_basic.npz  BasicDecoder.forward (basicCoders.py:28-42)
+  encoder.npz      HierarchicalEncoder.forward with GumbelMod, training and evaluation mode
+                   (hierarchicalEncoder.py:139-183, gumbelmod.py:14-24)
 """
 import os
 import sys
@@ -276,6 +278,50 @@ def gen_decoder():
     print("decoder_basic ok")
 
 
+def gen_encoder():
+    """The reference's HierarchicalEncoder (Gumbel smoother) fed the uniforms of the device contract."""
+    from types import SimpleNamespace
+    from models.networks.hierarchicalEncoder import HierarchicalEncoder
+    torch.manual_seed(33)
+    rng = np.random.default_rng(5)
+    B, n_in, n_lat, seed, beta = 20, 50, 16, 0x5EED + 11, 7.0
+    cfg = SimpleNamespace(model=SimpleNamespace(encoder_hidden_nodes=[40, 30], beta_smoothing_fct=beta))
+    enc = HierarchicalEncoder(activation_fct=torch.nn.ReLU(), input_dimension=n_in, n_latent_hierarchy_lvls=2,
+                              n_latent_nodes=n_lat, n_encoder_layer_nodes=24, n_encoder_layers=2, skip_latent_layer=False,
+                              smoother="Gumbel", cfg=cfg)
+    x = rng.standard_normal((B, n_in)).astype(np.float32)
+    levels = [[(m.weight.detach().numpy().copy(), m.bias.detach().numpy().copy()) for m in net if isinstance(m, torch.nn.Linear)]
+              for net in enc._networks]
+    out = dict(x=x, beta=beta, seed=seed, n_levels=len(levels), n_layers=len(levels[0]))
+    for li, ch in enumerate(levels):
+        for i, (W, b) in enumerate(ch):
+            out["L%d_W%d" % (li, i)] = W; out["L%d_b%d" % (li, i)] = b
+    for mode, is_training in (("train", True), ("eval", False)):
+        # training: the device's fp32 rho; evaluation: rho = 1 - u with the exact u (float64 promotes the compare)
+        def rho(lvl, shape):
+            u32 = dec.smooth_u32(seed, shape[0], shape[1], 0, 0, lvl * n_lat)
+            if is_training:
+                return dec.smooth_rho(u32)
+            return (1.0 - u32.astype(np.float64) / 4294967296.0).astype(np.float32)
+        calls = []
+        with RandInterposer(lambda i, s_: (calls.append(s_), torch.from_numpy(rho(i, s_)))[1]), torch.no_grad():
+            b_, logits, samples = enc(torch.from_numpy(x), is_training=is_training)
+        assert len(calls) == 2 and float(b_) == beta
+        ol, os_ = dec.encoder_forward(levels, x, beta, is_training, rho)
+        for lvl in range(2):
+            np.testing.assert_allclose(ol[lvl], logits[lvl].numpy(), rtol=1e-5, atol=1e-5)
+            if is_training:
+                np.testing.assert_allclose(os_[lvl], samples[lvl].numpy(), rtol=0, atol=2e-5)
+            out["%s_logits%d" % (mode, lvl)] = logits[lvl].numpy(); out["%s_samples%d" % (mode, lvl)] = samples[lvl].numpy()
+        pl, ps, clean = dec.encoder_forward_philox(levels, x, beta, is_training, seed)
+        if not is_training:
+            assert clean.mean() > 0.9
+            for lvl in range(2):
+                assert np.array_equal(ps[lvl][clean], samples[lvl].numpy()[clean]), lvl
+        print("encoder %s: mean sample %.3f" % (mode, np.mean([s_.numpy().mean() for s_ in samples])), "clean %.3f" % clean.mean())
+    np.savez_compressed(os.path.join(OUT, "encoder.npz"), **out)
+
+
 def main():
     _ref_shim.install()
     os.makedirs(OUT, exist_ok=True)
@@ -290,6 +336,7 @@ def main():
     gen_negphase()
     gen_port_check()
     gen_decoder()
+    gen_encoder()
 
 
 if __name__ == "__main__":

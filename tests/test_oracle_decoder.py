@@ -37,3 +37,28 @@ def test_hit_uniforms_follow_the_chain_offset():
     b = dec.hit_uniforms(7, 4, 40, chain_offset=6, step=3)
     assert np.array_equal(a[6:], b)
     assert not np.array_equal(a, dec.hit_uniforms(7, 10, 40, chain_offset=0, step=4))
+
+
+def _encoder_levels(g):
+    return [[(g["L%d_W%d" % (l, i)], g["L%d_b%d" % (l, i)]) for i in range(int(g["n_layers"]))] for l in range(int(g["n_levels"]))]
+
+
+def test_encoder_oracle_matches_reference_in_both_modes(golden):
+    """tests/golden/encoder.npz: the reference's HierarchicalEncoder.forward (Gumbel smoother) fed the uniforms of
+    the device contract; the restatement must reproduce logits and samples of every hierarchy level."""
+    g = golden("encoder")
+    levels, seed, beta = _encoder_levels(g), int(g["seed"]), float(g["beta"])
+    n_lat = levels[0][-1][0].shape[0]
+    for mode, is_training in (("train", True), ("eval", False)):
+        pl, ps, clean = dec.encoder_forward_philox(levels, g["x"], beta, is_training, seed)
+        for lvl in range(len(levels)):
+            np.testing.assert_allclose(pl[lvl], g["%s_logits%d" % (mode, lvl)], rtol=1e-5, atol=1e-5)
+            if is_training:
+                np.testing.assert_allclose(ps[lvl], g["%s_samples%d" % (mode, lvl)], rtol=0, atol=2e-5)
+            else:
+                assert clean.mean() > 0.9
+                assert np.array_equal(ps[lvl][clean], g["%s_samples%d" % (mode, lvl)][clean])
+    # the injected-rho form is the same function
+    rho = lambda lvl, shape: dec.smooth_rho(dec.smooth_u32(seed, shape[0], shape[1], 0, 0, lvl * n_lat))
+    pl2, ps2 = dec.encoder_forward(levels, g["x"], beta, True, rho)
+    np.testing.assert_allclose(ps2[1], g["train_samples1"], rtol=0, atol=2e-5)
