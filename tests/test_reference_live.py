@@ -106,3 +106,14 @@ def test_decoder_fixture_regenerates_identically(golden, tmp_path, monkeypatch):
         assert sorted(new) == sorted(old)
         for key in new:
             assert np.array_equal(new[key], old[key]), (name, key)
+
+
+def test_encoder_fixture_regenerates_identically(golden, tmp_path, monkeypatch):
+    from oracle import gen_golden
+    _ref_shim.install()
+    monkeypatch.setattr(gen_golden, "OUT", str(tmp_path))
+    gen_golden.gen_encoder()
+    new, old = dict(np.load(tmp_path / "encoder.npz")), golden("encoder")
+    assert sorted(new) == sorted(old)
+    for key in new:
+        assert np.array_equal(new[key], old[key]), key
