@@ -28,6 +28,7 @@ class PCD(BaseSampler):
                  **kwargs):
         super(PCD, self).__init__(**kwargs)
         self._RBM = RBM
+        self.__dict__["_rbm_plain"] = RBM      # same object, reachable without nn.Module.__getattr__ (hot path)
         self._batch_size = batch_size
         # pcd.py:16-17 draws the first state with CPU RNG; here the state is drawn on the
         # device at call time, so nothing is materialised until the first call.
@@ -73,12 +74,14 @@ class PCD(BaseSampler):
     # --------------------------------------------------------------------- k-step chain
     def _run_chain(self, v, init_chains, k, step_offset, stats_scale=None):
         lib = _lib.load()
-        dev = self._RBM.visible_bias.device
-        _lib.require_cuda(self._RBM.visible_bias, "RBM parameters")
+        rbm = self.__dict__.get("_rbm_plain")
+        if rbm is None or rbm is not self._modules.get("_RBM"):      # the submodule was replaced after construction
+            rbm = self.__dict__["_rbm_plain"] = self._RBM
         B = self._batch_size
-        nV, nH = self._RBM.weights.shape
         need_bf16 = self._variant != _lib.VARIANT_GENERAL
-        p, keep = self._pack.pack(self._RBM, need_bf16=need_bf16)
+        p, keep = self._pack.pack(rbm, need_bf16=need_bf16)     # raises for CPU parameters (no CPU fallback)
+        dev = keep[0].device
+        nV, nH = p.n_visible, p.n_hidden
         if v is None:
             v = torch.empty((B, nV), dtype=torch.float32, device=dev)
         h = torch.empty((B, nH), dtype=torch.float32, device=dev)
@@ -113,12 +116,12 @@ class PCD(BaseSampler):
         """Block Gibbs sampling (pcd.py:51-69). Returns (visible_states, hidden_states)."""
         k = self.n_gibbs_sampling_steps
         step_offset = self._half_steps
-        with torch.no_grad():
-            if self._persistent and self._MCState is not None:
-                out = self._run_chain(self._MCState.clone(), False, k, step_offset, _stats_scale)
-            else:
-                out = self._run_chain(None, True, k, step_offset, _stats_scale)
-        self._half_steps += 2 * k
+        # (no autograd involved: fresh output tensors filled by the library)
+        if self._persistent and self._MCState is not None:
+            out = self._run_chain(self._MCState.detach().clone(), False, k, step_offset, _stats_scale)
+        else:
+            out = self._run_chain(None, True, k, step_offset, _stats_scale)
+        self.__dict__["_half_steps"] = step_offset + 2 * k      # plain attribute write, not nn.Module.__setattr__
         if self._persistent:
             self._MCState = out[0]  # true PCD (the line the reference commented out, pcd.py:64)
         return out
