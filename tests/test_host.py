@@ -172,3 +172,42 @@ def test_modules_survive_pickle_and_deepcopy():
     assert s3.get_batch_size() == 4 and torch.equal(s3._RBM.weights, r.weights)
     assert pickle.loads(pickle.dumps(g)).n_gibbs_sampling_steps == 2
     s3.load_state_dict(s.state_dict())
+
+
+def test_decoder_and_encoder_runners_validate_on_the_host():
+    """DecoderRunner / EncoderRunner refuse what the B200 path does not implement, and CPU tensors (no CPU fallback)."""
+    import torch
+    from divae_b200.decoder import DecoderRunner, EncoderRunner
+
+    class Dec(torch.nn.Module):
+        def __init__(self, act):
+            super().__init__()
+            self._activation_fct = act
+            self._layers = torch.nn.ModuleList([torch.nn.Linear(4, 6), torch.nn.Linear(6, 5)])
+
+    with pytest.raises(RuntimeError, match="ReLU"):
+        DecoderRunner(Dec(torch.nn.Tanh()))
+    r = DecoderRunner(Dec(torch.nn.ReLU()))
+    assert (r.in_features, r.out_features, r.two_heads) == (4, 5, False)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        r(torch.zeros(3, 4))
+    with pytest.raises(RuntimeError, match="two-headed"):
+        r.shower(torch.zeros(3, 4), seed=1)
+    bad = Dec(torch.nn.ReLU()); bad._layers = torch.nn.ModuleList([torch.nn.Linear(4, 6, bias=False)])
+    with pytest.raises(RuntimeError, match="nn.Linear layers with bias"):
+        DecoderRunner(bad)
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self._networks = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.ReLU(), torch.nn.Linear(6, 3), torch.nn.Identity())])
+
+    with pytest.raises(RuntimeError, match="beta"):
+        EncoderRunner(Enc())
+    e = EncoderRunner(Enc(), beta=5.0)
+    assert e.n_latent == 3 and e.beta == 5.0
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        e(torch.zeros(2, 4))
+    tanh = Enc(); tanh._networks[0][1] = torch.nn.Tanh()
+    with pytest.raises(RuntimeError, match="Linear/ReLU"):
+        EncoderRunner(tanh, beta=5.0)
