@@ -9,8 +9,13 @@ import divae_b200
 from divae_b200.decoder import DecoderRunner
 from oracle import rbm_oracle as orc
 
+import os
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+# RBM_B200_FUZZ=<n> multiplies the number of cases and RBM_B200_FUZZ_SEED=<s> changes them (bug hunts; default: the fixed set)
+FUZZ = max(1, int(os.environ.get("RBM_B200_FUZZ", "1")))
+FUZZ_SEED = int(os.environ.get("RBM_B200_FUZZ_SEED", "0"))
 
 
 def make_rbm(W, a, c):
@@ -31,7 +36,7 @@ def random_cases(n, seed):
         yield nV, nH, B, k, int(rng.integers(1, 2 ** 31))
 
 
-@pytest.mark.parametrize("case", list(random_cases(14, 2024)))
+@pytest.mark.parametrize("case", list(random_cases(14 * FUZZ, 2024 + FUZZ_SEED)))
 def test_umma_chains_and_statistics_on_random_shapes(case):
     nV, nH, B, k, seed = case
     rng = np.random.default_rng(seed)
@@ -72,7 +77,7 @@ def decoder_cases(n, seed):
         yield widths, int(rng.choice([rng.integers(1, 300), rng.integers(300, 9000)])), int(rng.integers(1, 2 ** 31))
 
 
-@pytest.mark.parametrize("case", list(decoder_cases(8, 77)))
+@pytest.mark.parametrize("case", list(decoder_cases(8 * FUZZ, 77 + FUZZ_SEED)))
 def test_decoder_on_random_layouts(case):
     widths, B, seed = case
     torch.manual_seed(seed)
