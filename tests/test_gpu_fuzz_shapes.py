@@ -111,3 +111,31 @@ def test_decoder_on_random_layouts(case):
     assert abs(gate_rate - expect) < 5 * np.sqrt(0.25 / n_eff) + 2e-3
     close = ((s.double() - torch.relu(outs[1])).abs() / (1 + outs[1].abs()))[fired]
     assert close.numel() == 0 or close.max().item() <= 2e-4
+
+
+def small_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    for _ in range(n):
+        nV, nH = int(rng.integers(1, 257)), int(rng.integers(1, 257))
+        B = int(rng.choice([rng.integers(1, 40), rng.integers(40, 700), rng.integers(700, 9000)]))
+        yield nV, nH, B, int(rng.integers(1, 6)), int(rng.integers(1, 2 ** 31)), str(rng.choice(["smem", "general", "auto"]))
+
+
+@pytest.mark.parametrize("case", list(small_cases(12 * FUZZ, 9 + FUZZ_SEED)))
+def test_small_priors_on_random_shapes(case):
+    """Shared-memory / general / AUTO paths: chains against the oracle, negative-phase statistics exact."""
+    nV, nH, B, k, seed, variant = case
+    rng = np.random.default_rng(seed)
+    W = orc.round_bf16((rng.standard_normal((nV, nH)) * 0.5 / np.sqrt(max(nV, nH))).astype(np.float32))
+    a = (0.3 * rng.standard_normal(nV)).astype(np.float32)
+    c = (0.3 * rng.standard_normal(nH)).astype(np.float32)
+    s = divae_b200.PCD(batch_size=B, RBM=make_rbm(W, a, c), n_gibbs_sampling_steps=k, seed=seed, variant=variant)
+    v, h, (S, sv, sh), _e = s.block_gibbs_sampling(_stats_scale=1.0)
+    assert torch.equal(S.double(), v.double().t() @ h.double())
+    assert torch.equal(sv.double(), v.double().sum(0)) and torch.equal(sh.double(), h.double().sum(0))
+    n = min(B, 48)
+    for off in sorted({0, B - n}):
+        ov, oh, clean = orc.block_gibbs_philox(W, a, c, n, k, seed, chain_offset=off)
+        vn, hn = v[off:off + n].cpu().numpy(), h[off:off + n].cpu().numpy()
+        assert clean.mean() > 0.7
+        assert (vn[clean] == ov[clean]).all() and (hn[clean] == oh[clean]).all(), (case, off)
