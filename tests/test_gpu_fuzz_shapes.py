@@ -139,3 +139,32 @@ def test_small_priors_on_random_shapes(case):
         vn, hn = v[off:off + n].cpu().numpy(), h[off:off + n].cpu().numpy()
         assert clean.mean() > 0.7
         assert (vn[clean] == ov[clean]).all() and (hn[clean] == oh[clean]).all(), (case, off)
+
+
+def cd_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    for _ in range(n):
+        yield (int(rng.integers(1, 400)), int(rng.integers(1, 300)), int(rng.choice([rng.integers(1, 40), rng.integers(40, 1024), rng.integers(1025, 1500)])),
+               int(rng.integers(1, 4)), int(rng.integers(1, 2 ** 31)))
+
+
+@pytest.mark.parametrize("case", list(cd_cases(6 * FUZZ, 5 + FUZZ_SEED)))
+def test_cd_k_on_random_shapes(case):
+    """CD-k (cooperative kernel for batches <= 1024, multi-launch path above) against the oracle's restatement of
+    sandbox/rbm_standalone.py:75-121 with broadcast uniforms."""
+    from divae_b200.samplers.contrastiveDivergence import ContrastiveDivergence
+    nV, nH, B, k, seed = case
+    rng = np.random.default_rng(seed)
+    W = (rng.standard_normal((nV, nH)) * 0.1).astype(np.float32)
+    a = (0.1 * rng.standard_normal(nV)).astype(np.float32); c = (0.1 * rng.standard_normal(nH)).astype(np.float32)
+    v0 = (rng.random((B, nV)) > 0.5).astype(np.float32)
+    U = rng.random((k + 1, nH)).astype(np.float32)
+    cd = ContrastiveDivergence(nV, nH, 1e-3, 0.5, k, 1e-4, device=DEV, seed=1)
+    cd._weights.copy_(torch.from_numpy(W)); cd._visible_bias.copy_(torch.from_numpy(a)); cd._hidden_bias.copy_(torch.from_numpy(c))
+    loss = cd.contrastive_divergence(torch.from_numpy(v0).to(DEV), uniforms=torch.from_numpy(U).to(DEV))
+    st = orc.cd_k(v0, W, a, c, k, lambda i, s: U[i][None, :])
+    state = orc.cd_update(dict(W=W.copy(), a=a.copy(), c=c.copy(), dW=np.zeros_like(W), da=np.zeros_like(a), dc=np.zeros_like(c)), st)
+    np.testing.assert_allclose(loss.item(), st["recon_sse"], rtol=5e-4)
+    np.testing.assert_allclose(cd._weights.cpu().numpy(), state["W"], atol=5e-5)
+    np.testing.assert_allclose(cd._visible_bias.cpu().numpy(), state["a"], atol=5e-5)
+    np.testing.assert_allclose(cd._hidden_bias.cpu().numpy(), state["c"], atol=5e-5)
