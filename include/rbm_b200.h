@@ -159,7 +159,9 @@ RBM_B200_API int rbm_b200_negative_phase(const float *v, const float *h, int64_t
  * For priors of at most 64 x 64 units (every prior the reference's model configs build except
  * divae.yaml and the *_deep variant) the statistics are computed INSIDE the final sweep of the
  * persistent shared-memory kernel from the on-chip states (v^T h by tensor-core MMA, raw counts
- * added atomically, scaled once); larger priors run the statistics kernels right after the chain.
+ * added atomically, scaled once).  On the UMMA variant v^T h is a tcgen05 GEMM over the sampler's bf16
+ * state tiles (chains split over CTAs, integer counts added with red.global.add.f32: exact for at most
+ * 2^24 chains per call, more is refused); other shapes run the fp32 statistics kernels after the chain.
  * energy_exp (device scalar, may be NULL; needs the fp32 W): -(<W,S_vh> + a.S_v + c.S_h), i.e. the mean
  * energy of the batch when scale = 1/B — the value GumBolt.energy_exp returns for these samples.
  * Replaces gumbolt.py:102-104 / dvaepp.py:141-159 (sampler call + energy_exp on its samples). */
@@ -178,6 +180,8 @@ RBM_B200_API int rbm_b200_block_gibbs_stats(const rbm_b200_params *p, float *v, 
  *             else [k+1, n_hidden] fp32 rows, each broadcast over the batch like the reference's
  *             torch.rand(n_hidden) (rbm_standalone.py:72,84).
  *   W, vbias, hbias, dW, dvb, dhb  updated in place;  loss: device scalar;  k >= 1.
+ * Batches of at most 1024 rows run as ONE cooperative kernel launch (phases separated by grid barriers),
+ * larger ones as 3k + 4 launches; same arithmetic either way.
  * workspace: rbm_b200_cd_workspace(...) bytes. */
 RBM_B200_API size_t rbm_b200_cd_workspace(int32_t n_visible, int32_t n_hidden, int64_t B);
 RBM_B200_API int rbm_b200_cd_step(float *W, float *vbias, float *hbias, float *dW, float *dvb, float *dhb,
