@@ -195,24 +195,45 @@ class EncoderRunner:
     __call__ = forward
 
 
-def generate_samples(model, num_samples=64, true_energy=None, seed=0):
+def generate_samples(model, num_samples=64, true_energy=None, seed=0, group=None, gather=False):
     """Drop-in for GumBoltCaloV5.generate_samples (models/autoencoders/gumboltCaloV5.py:78-96).
 
     The reference loops `num_samples // batch_size` times over block_gibbs_sampling() + decoder; here the chains
     of all iterations are drawn in ONE sampler launch (`PCD.sample`) and decoded in one pass.  Returns
-    (true_energies [n,1], samples [n, n_out]) with n = max(num_samples // batch_size, 1) * batch_size."""
+    (true_energies [n,1], samples [n, n_out]) with n = max(num_samples // batch_size, 1) * batch_size.
+
+    With torch.distributed initialised (or `group` given) the n showers are sharded over the ranks as contiguous
+    blocks of global shower ids (dist.shard_chains): every rank returns ITS block (or, with gather=True, all of
+    them); because the sampler's and the hit gate's draws are keyed by the global id, the union of the blocks is
+    what a single GPU would have generated.  Random conditioning energies (true_energy=None) are drawn per rank from
+    torch's generator and are therefore not part of that guarantee."""
     sampler = model.sampler
     bs = sampler.get_batch_size()
     n = max(num_samples // bs, 1) * bs
-    v, h = sampler.sample(n)
+    off, n_local = 0, n
+    distributed = group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())
+    if distributed:
+        from . import dist as _dist
+        rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+        off, n_local = _dist.shard_chains(n, rank, world)
+    v, h = sampler.sample(n_local, first_chain=off)
     if true_energy is None:
-        true_e = torch.rand((n, 1), device=v.device) * 100.
+        true_e = torch.rand((n_local, 1), device=v.device) * 100.
     else:
-        true_e = torch.ones((n, 1), device=v.device) * true_energy
+        true_e = torch.ones((n_local, 1), device=v.device) * true_energy
     # one runner per model: it keeps the split parameters staged on the device between calls
     runner = getattr(model, "_b200_decoder_runner", None)
     if runner is None or runner._decoder is not model.decoder:
         runner = DecoderRunner(model.decoder)
         object.__setattr__(model, "_b200_decoder_runner", runner)
     x = torch.cat([v, h, true_e], dim=1)
-    return true_e, runner.shower(x, seed=seed)
+    samples = runner.shower(x, seed=seed, chain_offset=off)
+    if distributed and gather:
+        world = torch.distributed.get_world_size(group)
+        sizes = [_dist.shard_chains(n, r, world)[1] for r in range(world)]
+        outs_e = [torch.empty((m, 1), device=v.device) for m in sizes]
+        outs_s = [torch.empty((m, samples.shape[1]), device=v.device) for m in sizes]
+        torch.distributed.all_gather(outs_e, true_e.contiguous(), group=group)
+        torch.distributed.all_gather(outs_s, samples.contiguous(), group=group)
+        return torch.cat(outs_e, 0), torch.cat(outs_s, 0)
+    return true_e, samples

@@ -140,8 +140,11 @@ class PCD(BaseSampler):
                        "block_gibbs_injected")
         return v, h
 
-    def sample(self, n_samples, n_gibbs_sampling_steps=None):
+    def sample(self, n_samples, n_gibbs_sampling_steps=None, first_chain=0):
         """Draw `n_samples` independent chains in ONE launch (fresh Bernoulli(1/2) starts).
+
+        `first_chain` shifts the chain ids: a rank that draws chains [first_chain, first_chain + n_samples) of a
+        larger job gets exactly that slice of the unsharded result (generation sharded over GPUs).
 
         The calorimeter models generate `num_samples` showers by calling block_gibbs_sampling()
         `num_samples // batch_size` times in a Python loop, once per conditioning energy
@@ -152,7 +155,7 @@ class PCD(BaseSampler):
         saved = (self._batch_size, self._chain_offset, self._workspace)
         try:
             self._batch_size = int(n_samples)
-            self._chain_offset = saved[1] + saved[0]
+            self._chain_offset = saved[1] + saved[0] + int(first_chain)
             self._workspace = None
             with torch.no_grad():
                 v, h = self._run_chain(None, True, k, self._half_steps)

@@ -47,6 +47,35 @@ def main():
         rbm.zero_grad()
         (-e).backward()
         torch.testing.assert_close(rbm._weights.grad, Sf, rtol=0, atol=1e-6)
+    # shower generation sharded over the ranks: the gathered blocks equal the single-GPU generation
+    from divae_b200.decoder import generate_samples
+
+    class _V3(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self._activation_fct = torch.nn.ReLU()
+            self._layers = torch.nn.ModuleList([torch.nn.Linear(129, 200), torch.nn.Linear(200, 300)])
+            self._layers2 = torch.nn.ModuleList([torch.nn.Linear(300, 400), torch.nn.Linear(400, 504)])
+            self._layers3 = torch.nn.ModuleList([torch.nn.Linear(300, 400), torch.nn.Linear(400, 504)])
+
+    class _Model:
+        pass
+
+    torch.manual_seed(5)
+    model = _Model()
+    model.sampler = divae_b200.PCD(batch_size=128, RBM=divae_b200.RBM(64, 64).to(dev), n_gibbs_sampling_steps=10, seed=9)
+    model.decoder = _V3().to(dev)
+    single = _Model()
+    single.sampler = divae_b200.PCD(batch_size=128, RBM=model.sampler._RBM, n_gibbs_sampling_steps=10, seed=9)
+    single.decoder = model.decoder
+    g1 = None                                        # a one-rank group = the unsharded job on this GPU
+    for r in range(world):                           # (new_group is collective: every rank creates every group)
+        g = dist.new_group([r])
+        if r == rank:
+            g1 = g
+    e_full, s_full = generate_samples(single, num_samples=1024, true_energy=40.0, seed=3, group=g1)
+    e_all, s_all = generate_samples(model, num_samples=1024, true_energy=40.0, seed=3, gather=True)
+    assert s_all.shape == (1024, 504) and torch.equal(s_all, s_full) and torch.equal(e_all, e_full)
     # AIS: sharded estimate equals the unsharded one (same global chain ids)
     rbm = divae_b200.RBM(96, 64)
     with torch.no_grad():
@@ -70,7 +99,7 @@ def main():
     assert abs(z_sharded - z_single) < 1e-9, (z_sharded, z_single)
     dist.barrier()
     if rank == 0:
-        print("multi-GPU checks ok on %d GPUs: shards == slices, allreduced stats == single-GPU stats, AIS log Z %.6f" % (world, z_sharded))
+        print("multi-GPU checks ok on %d GPUs: shards == slices, allreduced stats == single-GPU stats, sharded generation == single-GPU generation, AIS log Z %.6f" % (world, z_sharded))
     dist.destroy_process_group()
 
 
