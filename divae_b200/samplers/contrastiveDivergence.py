@@ -95,7 +95,6 @@ class ContrastiveDivergence(object):
     def contrastive_divergence(self, input_data, uniforms=None):
         """One CD-k update (rbm_standalone.py:75-121) as ONE library call (rbm_b200_cd_step).
         Returns the summed squared reconstruction error (a 0-d tensor on the device)."""
-        import ctypes
         _lib.require_cuda(input_data, "input data")
         lib = _lib.load()
         v0 = input_data.float().contiguous()

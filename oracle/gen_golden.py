@@ -26,7 +26,7 @@ import sys
 import numpy as np
 import torch
 
-from . import _ref_shim, decoder_oracle as dec, philox, rbm_oracle as orc, ref_torch_port as port
+from . import _ref_shim, decoder_oracle as dec, rbm_oracle as orc, ref_torch_port as port
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
