@@ -10,8 +10,9 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librbm_b200.so")
 
-VARIANT_AUTO, VARIANT_GENERAL, VARIANT_SMEM, VARIANT_UMMA = 0, 1, 2, 3
-VARIANTS = {"auto": VARIANT_AUTO, "general": VARIANT_GENERAL, "smem": VARIANT_SMEM, "umma": VARIANT_UMMA}
+VARIANT_AUTO, VARIANT_GENERAL, VARIANT_SMEM, VARIANT_UMMA, VARIANT_UMMA_SPLIT = 0, 1, 2, 3, 4
+VARIANTS = {"auto": VARIANT_AUTO, "general": VARIANT_GENERAL, "smem": VARIANT_SMEM, "umma": VARIANT_UMMA,
+            "umma_split": VARIANT_UMMA_SPLIT}
 MODE_SAMPLE, MODE_INJECTED, MODE_PROBS = 0, 1, 2
 ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_NO_DEVICE = -1, -2, -3, -4
 

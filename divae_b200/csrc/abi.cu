@@ -25,9 +25,11 @@ int cuda_fail(cudaError_t e, const char* what) {
 int get_device_info(DeviceInfo* out) {
   static DeviceInfo cache[64];
   static bool valid[64] = {};
+  static std::mutex mu;
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  std::lock_guard<std::mutex> lock(mu);
   if (dev >= 0 && dev < 64 && valid[dev]) { *out = cache[dev]; return 0; }
   DeviceInfo d{};
   d.device = dev;
@@ -82,6 +84,7 @@ static int require_device() {
 // 256 units when chains are few (256x256 x 1024 chains: 0.11 ms vs 0.54 ms per call); with many
 // chains the tcgen05 GEMM wins at 256 units (7.0e11 vs 5.6e11).
 int pick_variant(const rbm_b200_params* p, int64_t B, int variant) {
+  if (variant == RBM_B200_VARIANT_UMMA_SPLIT) return RBM_B200_VARIANT_UMMA;
   if (variant != RBM_B200_VARIANT_AUTO) return variant;
   const int nmax = p->n_visible > p->n_hidden ? p->n_visible : p->n_hidden;
   if (p->W_bf16 && smem_variant_supported(p->n_visible, p->n_hidden) && (nmax <= 128 || B < 8192))
@@ -160,7 +163,7 @@ static int block_gibbs_impl(const rbm_b200_params* p, float* v, float* h, int64_
   if (rc) return rc;
   RBM_REQUIRE(B >= 0 && k >= 0, RBM_B200_ERR_INVALID, "negative batch or step count");
   RBM_REQUIRE(B == 0 || (v && h), RBM_B200_ERR_INVALID, "state pointer is NULL");
-  RBM_REQUIRE(variant >= RBM_B200_VARIANT_AUTO && variant <= RBM_B200_VARIANT_UMMA, RBM_B200_ERR_INVALID,
+  RBM_REQUIRE(variant >= RBM_B200_VARIANT_AUTO && variant <= RBM_B200_VARIANT_UMMA_SPLIT, RBM_B200_ERR_INVALID,
               "unknown variant %d", variant);
   if ((rc = require_device())) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -174,11 +177,13 @@ static int block_gibbs_impl(const rbm_b200_params* p, float* v, float* h, int64_
                             workspace_bytes, st, fuse ? S_vh : nullptr, fuse ? S_v : nullptr, fuse ? S_h : nullptr);
   }
   if (chosen == RBM_B200_VARIANT_UMMA) {
-    RBM_REQUIRE(p->W_bf16, RBM_B200_ERR_INVALID, "UMMA variant needs W_bf16");
+    const bool split = variant == RBM_B200_VARIANT_UMMA_SPLIT;
+    if (split) RBM_REQUIRE(p->W, RBM_B200_ERR_INVALID, "UMMA_SPLIT variant needs the fp32 W");
+    else RBM_REQUIRE(p->W_bf16, RBM_B200_ERR_INVALID, "UMMA variant needs W_bf16");
     const bool fuse = S_vh != nullptr && k > 0;
     if (stats_fused) *stats_fused = fuse;
     return umma_block_gibbs(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, workspace,
-                            workspace_bytes, st, fuse ? S_vh : nullptr, fuse ? S_v : nullptr, fuse ? S_h : nullptr);
+                            workspace_bytes, st, fuse ? S_vh : nullptr, fuse ? S_v : nullptr, fuse ? S_h : nullptr, split);
   }
   RBM_REQUIRE(p->W, RBM_B200_ERR_INVALID, "GENERAL variant needs fp32 W");
   if (init_chains) {
@@ -311,7 +316,7 @@ int rbm_b200_ais_run(const rbm_b200_params* p, int64_t n_chains, const double* b
                      void* stream) {
   int rc = check_params(p, false);
   if (rc) return rc;
-  RBM_REQUIRE(p->W_bf16 != nullptr, RBM_B200_ERR_INVALID, "AIS needs W_bf16");
+  RBM_REQUIRE(p->W_bf16 != nullptr || p->W != nullptr, RBM_B200_ERR_INVALID, "AIS needs W_bf16, or the fp32 W for split weights");
   RBM_REQUIRE(n_chains >= 0, RBM_B200_ERR_INVALID, "negative chain count");
   RBM_REQUIRE(betas != nullptr && n_betas >= 2, RBM_B200_ERR_INVALID, "need at least two betas");
   RBM_REQUIRE(betas[0] == 0.0 && betas[n_betas - 1] == 1.0, RBM_B200_ERR_INVALID, "betas must run from 0 to 1");
@@ -320,8 +325,9 @@ int rbm_b200_ais_run(const rbm_b200_params* p, int64_t n_chains, const double* b
   if (n_chains == 0) return 0;
   RBM_REQUIRE(logw != nullptr, RBM_B200_ERR_INVALID, "logw is NULL");
   if ((rc = require_device())) return rc;
+  // W_bf16 == NULL: the fp32 W is carried as bf16 high + low parts (fp32-grade pre-activations, K axis doubled)
   return umma_ais_run(p, n_chains, betas, n_betas, seed, chain_offset, logw, workspace, workspace_bytes,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, p->W_bf16 == nullptr);
 }
 
 size_t rbm_b200_decoder_workspace(const rbm_b200_decoder* d, int64_t B) {

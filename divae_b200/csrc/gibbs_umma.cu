@@ -19,185 +19,10 @@
 // (umma_block_gibbs, umma_ais_run).
 #include <vector>
 
-#include "umma_common.cuh"
+#include "umma_chain.cuh"
 
 namespace rbm {
 namespace {
-
-// ---------------------------------------------------------------------------------------------------
-// Multi-step variant: ALL half-steps of a chain block in ONE launch, for jobs whose per-half-step grid
-// would not fill the GPU (few chains: PCD batches, AIS shards).  A cluster of n_tiles CTAs owns one
-// 128-chain row block for the whole run; CTA `n_blk` computes output tile n_blk of every half-step.
-// Between half-steps only that row block's CTAs have to agree (rows are independent), so the only
-// synchronisation is ONE cluster barrier per half-step after the state tile has been stored - no
-// relaunch, no grid-wide sync, and the draw context / annealing schedule advance in registers.
-struct MultiArgs {
-  const float* nbias[2];   // [dir]: dir 0 = v->h (hidden biases), dir 1 = h->v
-  int ldo[2];              // padded unit count of the state WRITTEN by dir
-  int n_valid[2];
-  int n_tiles[2];
-  int k_blocks[2];
-  int steps;               // number of half-steps in this launch
-  int first_dir;
-  uint64_t seed, chain_offset, step_offset;   // half-step t draws with counter step_offset + t
-  uint32_t tag;
-  const float* betas;      // annealed flavours: beta index of half-step t is 1 + t/2
-  float* wpart;            // AIS: [rows, wpart_ld] log-weight partials (log2 units), added to at the end
-  int wpart_ld;
-  uint32_t kf_magic;       // kKfMagic (see EpiParams)
-};
-
-template <int BLOCK_N, int EPI0, int EPI1>
-__global__ void __launch_bounds__(kNumThreads, 1)
-umma_multistep_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
-                      const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ CUtensorMap tm_b1,
-                      const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1,
-                      const MultiArgs args) {
-  using L = SmemLayout<BLOCK_N, 1>;
-  constexpr int kStages = L::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + L::kBarOffset;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kBarOffset + 8 * (2 * kStages + 4));
-
-  const int warp_idx = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int n_blk = (int)cluster_ctarank();                     // output tile of this CTA
-  uint32_t cs;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(cs));
-  const int m_blk = (int)(blockIdx.x / cs);                      // the cluster's 128-chain row block
-  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;    // one accumulator (steps are serialised)
-
-  if (warp_idx == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a0) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a1) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b0) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b1) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_o0) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_o1) : "memory");
-  }
-  if (warp_idx == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp_idx == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  const int quarter = warp_idx & 3;
-  const int cq = (warp_idx - 4) >> 2;
-  const uint32_t stage_warp = smem_base + L::kStoreOffset + (uint32_t)(warp_idx >= 4 ? warp_idx - 4 : 0) * kStoreWarpBytes;
-  const int row_base = m_blk * BLOCK_M + quarter * 32;
-  const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)(row_base + lane));
-  int stage = 0; uint32_t phase = 0;     // smem ring position (producer lane and MMA lane each keep their own copy)
-  int it = 0;                            // number of tiles this CTA has processed (accumulator barrier parity)
-  float wsum = 0.f;
-
-  for (int t = 0; t < args.steps; ++t) {
-    const int dir = (args.first_dir + t) & 1;
-    const bool active = n_blk < args.n_tiles[dir];
-    if (active) {
-      const CUtensorMap* tm_a = dir ? &tm_a1 : &tm_a0;
-      const CUtensorMap* tm_b = dir ? &tm_b1 : &tm_b0;
-      if (warp_idx == 0) {
-        {
-          // ---- TMA producer: this row block's state (A) and tile n_blk of W (B: MN-major for dir 0, K-major for dir 1)
-          for (int kb = 0; kb < args.k_blocks[dir]; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage * L::kStageBytes;
-            const uint32_t sb = sa + kABytes;
-            if (elect_one_sync()) {
-              mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
-              tma_load_2d(sa, tm_a, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
-              if (dir == 0) {
-#pragma unroll
-                for (int nb = 0; nb < BLOCK_N / 64; ++nb)
-                  tma_load_2d(sb + nb * (BLOCK_K * 128), tm_b, full_bar(stage), n_blk * BLOCK_N + nb * 64, kb * BLOCK_K);
-              } else {
-                tma_load_2d(sb, tm_b, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
-              }
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-      } else if (warp_idx == 1) {
-        {
-          // ---- MMA issuer (the accumulator is free: the previous half-step ended with a cluster barrier).
-          // Whole warp, warp-uniform; one elected lane issues (see umma_half_step_kernel).
-          const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, dir == 0);
-          for (int kb = 0; kb < args.k_blocks[dir]; ++kb) {
-            mbar_wait(full_bar(stage), phase);
-            tcgen05_fence_after();
-            const uint32_t sa = smem_base + stage * L::kStageBytes;
-            const uint32_t sb = sa + kABytes;
-            if (elect_one_sync()) {
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                const uint64_t adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-                const uint64_t bdesc = dir == 0 ? make_smem_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                                : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-                umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-              }
-              umma_commit(empty_bar(stage));
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
-          if (elect_one_sync()) umma_commit(tmem_full_bar);
-          __syncwarp();
-        }
-      } else if (warp_idx >= 4) {
-        // ---- epilogue
-        EpiParams ep;
-        ep.nbias = args.nbias[dir]; ep.ldo = args.ldo[dir]; ep.n_valid = args.n_valid[dir];
-        ep.ctx = make_draw_ctx(args.seed, args.step_offset + (uint64_t)t, args.tag);
-        ep.scale = -1.4426950408889634f; ep.bmul = 1.f; ep.ratio = 0.f; ep.debug_mode = 0;
-        ep.kf_magic = args.kf_magic;
-        if (EPI0 != EPI_GIBBS) {
-          const float bk = __ldg(args.betas + 1 + (t >> 1)), bkm1 = __ldg(args.betas + (t >> 1));
-          ep.scale = -1.4426950408889634f * bk;
-          ep.bmul = dir == 0 ? bk : 1.f;
-          ep.ratio = bkm1 / bk;
-        }
-        auto wait_full = [&] { mbar_wait(tmem_full_bar, (uint32_t)it & 1u); };
-        auto release = [] {};
-        const CUtensorMap* tm_o = dir ? &tm_o1 : &tm_o0;
-        if (dir == 0) epilogue_tile<BLOCK_N, EPI0>(ep, tm_o, tmem_base, n_blk, row_base, chain, quarter, cq, lane, stage_warp, wsum, wait_full, release);
-        else epilogue_tile<BLOCK_N, EPI1>(ep, tm_o, tmem_base, n_blk, row_base, chain, quarter, cq, lane, stage_warp, wsum, wait_full, release);
-        if (lane == 0) tma_store_wait_all();       // this CTA's part of the new state is in global memory
-      }
-      ++it;
-    }
-    // ---- end of the half-step: every CTA of the row block has stored its tile before anyone reads the new state
-    __syncwarp();
-    asm volatile("fence.proxy.async;" ::: "memory");
-    tcgen05_fence_before();
-    cluster_sync_all();
-    tcgen05_fence_after();
-    asm volatile("fence.proxy.async;" ::: "memory");
-  }
-  if (EPI0 == EPI_AIS_WEIGHT && warp_idx >= 4 && n_blk < args.n_tiles[0]) {
-    float* slot_ptr = args.wpart + (size_t)(row_base + lane) * args.wpart_ld + (n_blk * kEpiSets + cq);
-    *slot_ptr += wsum;
-  }
-  __syncthreads();
-  if (warp_idx == 2) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-  }
-}
 
 // ------------------------------------------------------------- helper kernels
 // fp32 [B, n] (row pitch n) -> bf16 [rows_pad, ld] zero padded
@@ -236,6 +61,17 @@ __global__ void pad_w_kernel(const uint16_t* __restrict__ W, uint16_t* __restric
   if (idx >= (int64_t)nVp * nHp) return;
   const int i = (int)(idx / nHp), j = (int)(idx % nHp);
   Wp[idx] = (i < nV && j < nH) ? W[(int64_t)i * nH + j] : (uint16_t)0;
+}
+// split weights: W = high + low with high = bf16(W), low = bf16(W - high); both zero padded
+__global__ void pad_w_split_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Whi, __nv_bfloat16* __restrict__ Wlo,
+                                   int nV, int nH, int nVp, int nHp) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)nVp * nHp) return;
+  const int i = (int)(idx / nHp), j = (int)(idx % nHp);
+  const float w = (i < nV && j < nH) ? W[(int64_t)i * nH + j] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  Whi[idx] = hi;
+  Wlo[idx] = __float2bfloat16_rn(w - __bfloat162float(hi));
 }
 __global__ void nbias_kernel(const float* __restrict__ bias, float* __restrict__ nb, int n, int n_pad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -480,12 +316,48 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int64_t B, int ld, int n
 // ------------------------------------------------------------------ host side
 constexpr int kMaxDeviceBetas = 1 << 18;   // longer AIS schedules fall back to one launch per half-step
 
+// Tile shape of the chain kernel: one BLOCK_N for both directions, single CTAs or CTA pairs (256-wide tiles only)
+struct ChainCfg { int bn, ctas; };
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Measured on B200 (profiles/r02_chain_tile_sweep.txt): wide tiles and CTA pairs stage the fewest shared-memory bytes
+// per flop and win once every CTA has several items per half-step in flight; with few chains narrower tiles
+// keep all SMs busy and shorten the per-half-step dependency chain (TMA store -> flag -> TMA load -> MMA -> epilogue).
+ChainCfg pick_chain_cfg(int nVp, int nHp, int64_t rows_pad, int sm_count) {
+  static const int force_bn = env_int("RBM_B200_CHAIN_BN", 0);
+  static const int force_pairs = env_int("RBM_B200_CHAIN_PAIRS", -1);
+  auto cols = [&](int bn) { return round_up(nVp, bn) + round_up(nHp, bn); };
+  auto items = [&](int bn) { return (rows_pad / BLOCK_M) * (int64_t)std::min(ceil_div(nVp, bn), ceil_div(nHp, bn)); };
+  ChainCfg c{64, 1};
+  if (force_bn == 64 || force_bn == 128 || force_bn == 256) {
+    c.bn = force_bn;
+  } else {
+    // fewest padded columns first; then the widest tile that still gives every SM >= 2 items per half-step
+    const int best = std::min(cols(64), std::min(cols(128), cols(256)));
+    for (int bn : {256, 128, 64}) {
+      if (cols(bn) != best) continue;
+      c.bn = bn;
+      if (items(bn) >= 2 * (int64_t)sm_count) break;
+    }
+  }
+  c.ctas = 1;
+  if (c.bn == 256 && pairs_enabled()) {
+    const bool many = items(256) >= 8 * (int64_t)sm_count;
+    if (force_pairs == 1 || (force_pairs == -1 && many)) c.ctas = 2;
+  }
+  return c;
+}
+
 struct Plan {
   int nV, nH, nVp, nHp;      // padded to multiples of 64
   int64_t rows_pad;          // chains padded to a multiple of 256 (one CTA-pair tile)
-  int bn_h, bn_v;            // BLOCK_N for the v->h and h->v half-steps
-  size_t off_W, off_nbh, off_nbv, off_V, off_H, off_wpart, off_betas, total;
-  int wpart_ld;              // AIS log-weight partial slots per chain: 4 per hidden-side N tile
+  int bn_h, bn_v;            // BLOCK_N of the per-half-step launches (v->h, h->v)
+  size_t off_W, off_Wlo, off_nbh, off_nbv, off_V, off_H, off_wpart, off_betas, off_flags, total;
+  int wpart_ld;              // AIS log-weight slots per chain: one per 32 hidden units
 };
 
 Plan make_plan(int nV, int nH, int64_t B) {
@@ -497,46 +369,65 @@ Plan make_plan(int nV, int nH, int64_t B) {
   auto align = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
   size_t o = 0;
   p.off_W = o; o = align(o + (size_t)p.nVp * p.nHp * 2);
+  p.off_Wlo = o; o = align(o + (size_t)p.nVp * p.nHp * 2);       // low part of split weights (W - bf16(W))
   p.off_nbh = o; o = align(o + (size_t)round_up(p.nHp, 256) * 4);
   p.off_nbv = o; o = align(o + (size_t)round_up(p.nVp, 256) * 4);
   p.off_V = o; o = align(o + (size_t)p.rows_pad * p.nVp * 2);
   p.off_H = o; o = align(o + (size_t)p.rows_pad * p.nHp * 2);
-  p.wpart_ld = kEpiSets * ceil_div(p.nHp, p.bn_h);
+  p.wpart_ld = p.nHp / 32;
   p.off_wpart = o; o = align(o + (size_t)p.rows_pad * p.wpart_ld * 4);
-  p.off_betas = o; o = align(o + (size_t)kMaxDeviceBetas * 4);   // AIS schedule for the multi-step kernel
+  p.off_betas = o; o = align(o + (size_t)kMaxDeviceBetas * 4);   // AIS schedule for the chain kernel
+  p.off_flags = o; o = align(o + (size_t)(p.rows_pad / BLOCK_M) * 4);   // row-block arrival counters (chain kernel)
   p.total = o + 1024;  // slack to align the caller's pointer
   return p;
 }
 
-// cluster sizes the multi-step kernel is launched with (one CTA per output tile of a row block)
-bool multistep_cluster_ok(int cs) { return cs == 1 || cs == 2 || cs == 4 || cs == 8; }
-
-// -1: automatic (one wave of CTAs), 0: never, 1: whenever the shape allows
-int multistep_mode() {
-  static const int mode = [] { const char* e = getenv("RBM_B200_MULTISTEP"); return e ? atoi(e) : -1; }();
-  return mode;
+// 1 (default): all half-steps in one dataflow launch (umma_chain.cuh); 0: one launch per half-step (round-1 path, A/B only)
+bool chain_enabled() {
+  static const bool on = env_int("RBM_B200_CHAIN", 1) != 0;
+  return on;
 }
 
-template <int BLOCK_N, int EPI0, int EPI1>
-int launch_multistep(const CUtensorMap* tm, const MultiArgs& a, int m_tiles, int cs, cudaStream_t st) {
-  auto kern = umma_multistep_kernel<BLOCK_N, EPI0, EPI1>;
-  using L = SmemLayout<BLOCK_N, 1>;
-  DeviceInfo di;
-  int rc = get_device_info(&di);
-  if (rc) return rc;
-  if ((rc = ensure_dynamic_smem(kern, di.device, L::kTotal))) return rc;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(m_tiles * cs));
-  cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = L::kTotal;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  RBM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], a));
-  return check_launch("umma_multistep_kernel");
+// Launches the chain kernel over `steps` half-steps starting with direction 0.
+//   W_lo != nullptr: split weights (bf16 high + bf16 low part), K axis doubled
+template <int EPI0, int EPI1>
+int run_chain(const Plan& pl, uint16_t* Wp, uint16_t* Wlo, const float* nbh, const float* nbv, __nv_bfloat16* Vs,
+              __nv_bfloat16* Hs, uint32_t* flags, int steps, uint64_t seed, uint64_t chain_offset, uint64_t step_offset,
+              uint32_t tag, const float* betas_dev, float* wpart, int sm_count, cudaStream_t st) {
+  const ChainCfg cfg = pick_chain_cfg(pl.nVp, pl.nHp, pl.rows_pad, sm_count);
+  const bool split = Wlo != nullptr;
+  int rc;
+  CUtensorMap tm[8];
+  if ((rc = make_tmap(&tm[0], Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
+  if ((rc = make_tmap(&tm[1], Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
+  // W is read MN-major (v->h: [64 k x 64 n] boxes) and K-major (h->v: [n rows x 64] boxes; a CTA of a pair stages half)
+  const uint32_t kbox = (uint32_t)(cfg.bn / cfg.ctas);
+  if ((rc = make_tmap(&tm[2], Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&tm[3], Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, kbox))) return rc;
+  if ((rc = make_tmap(&tm[4], split ? Wlo : Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&tm[5], split ? Wlo : Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, kbox))) return rc;
+  // epilogue stores: [32 chains x 32 units] boxes, 64-byte swizzle
+  if ((rc = make_tmap(&tm[6], Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_tmap(&tm[7], Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  ChainArgs a{};
+  a.nbias[0] = nbh; a.nbias[1] = nbv; a.ldo[0] = pl.nHp; a.ldo[1] = pl.nVp;
+  a.n_valid[0] = pl.nH; a.n_valid[1] = pl.nV;
+  a.n_tiles[0] = ceil_div(pl.nHp, cfg.bn); a.n_tiles[1] = ceil_div(pl.nVp, cfg.bn);
+  a.split_k[0] = pl.nVp / BLOCK_K; a.split_k[1] = pl.nHp / BLOCK_K;
+  a.k_blocks[0] = a.split_k[0] * (split ? 2 : 1); a.k_blocks[1] = a.split_k[1] * (split ? 2 : 1);
+  a.m_groups = (int)(pl.rows_pad / (BLOCK_M * cfg.ctas));
+  a.steps = steps; a.first_dir = 0; a.seed = seed; a.chain_offset = chain_offset; a.step_offset = step_offset;
+  a.tag = tag; a.betas = betas_dev; a.wpart = wpart; a.wpart_ld = pl.wpart_ld; a.kf_magic = kKfMagic; a.flags = flags;
+  RBM_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)(pl.rows_pad / BLOCK_M) * 4, st));
+  // every cluster must be resident (items wait for lower-numbered items of other clusters)
+  static const int grid_cap = env_int("RBM_B200_CHAIN_GRID", 0);
+  int64_t total_items = 0;
+  for (int t = 0; t < std::min(steps, 2); ++t) total_items += (int64_t)a.m_groups * a.n_tiles[t & 1];
+  if (steps > 2) total_items = (int64_t)1 << 40;
+  int grid = sm_count / cfg.ctas;
+  if (grid_cap > 0) grid = std::min(grid, grid_cap);
+  grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, total_items));
+  return launch_chain<EPI0, EPI1>(cfg.bn, cfg.ctas, split, tm, a, grid, st);
 }
 
 template <int BLOCK_N>
@@ -589,7 +480,7 @@ size_t umma_workspace_bytes(int nV, int nH, int64_t B) { return make_plan(nV, nH
 
 int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains,
                      uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws, size_t ws_bytes,
-                     cudaStream_t st, float* S_vh, float* S_v, float* S_h) {
+                     cudaStream_t st, float* S_vh, float* S_v, float* S_h, bool split_w) {
   const Plan pl = make_plan(p->n_visible, p->n_hidden, B);
   RBM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, RBM_B200_ERR_WORKSPACE,
               "UMMA variant needs %zu bytes of workspace, got %zu", pl.total, ws_bytes);
@@ -603,15 +494,20 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
 
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   uint16_t* Wp = reinterpret_cast<uint16_t*>(base + pl.off_W);
+  uint16_t* Wlo = split_w ? reinterpret_cast<uint16_t*>(base + pl.off_Wlo) : nullptr;
   float* nbh = reinterpret_cast<float*>(base + pl.off_nbh);
   float* nbv = reinterpret_cast<float*>(base + pl.off_nbv);
   __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(base + pl.off_V);
   __nv_bfloat16* Hs = reinterpret_cast<__nv_bfloat16*>(base + pl.off_H);
 
-  // stage parameters: padded bf16 W, pre-scaled biases
+  // stage parameters: padded bf16 W (or its high + low parts from the fp32 W), pre-scaled biases
   {
     const int64_t n = (int64_t)pl.nVp * pl.nHp;
-    pad_w_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W_bf16, Wp, pl.nV, pl.nH, pl.nVp, pl.nHp);
+    if (split_w)
+      pad_w_split_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W, reinterpret_cast<__nv_bfloat16*>(Wp),
+                                                                      reinterpret_cast<__nv_bfloat16*>(Wlo), pl.nV, pl.nH, pl.nVp, pl.nHp);
+    else
+      pad_w_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W_bf16, Wp, pl.nV, pl.nH, pl.nVp, pl.nHp);
     const int nh256 = round_up(pl.nHp, 256), nv256 = round_up(pl.nVp, 256);
     nbias_kernel<<<ceil_div(nh256, 256), 256, 0, st>>>(p->hbias, nbh, pl.nH, nh256);
     nbias_kernel<<<ceil_div(nv256, 256), 256, 0, st>>>(p->vbias, nbv, pl.nV, nv256);
@@ -628,74 +524,38 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   int rc = check_launch("umma staging kernels");
   if (rc) return rc;
 
-  // Chains are independent, so the k-step loop MAY run chunk by chunk (RBM_B200_CHUNK_ROWS), e.g. with chunks
-  // whose two state tiles fit in L2 so that half-steps stop round-tripping through HBM.  Measured on B200
-  // (profiles/r01_pairs_vs_single.txt): at config 4 it is a LOSS (158 vs 141 us per launch-equivalent for
-  // 18,944-chain chunks) - the per-launch overheads of 3.5x more, 3.5x smaller launches outweigh the HBM
-  // energy saved - so the default is one chunk.
-  int64_t chunk_rows = pl.rows_pad;
-  {
-    static const long env_chunk = [] { const char* e = getenv("RBM_B200_CHUNK_ROWS"); return e ? atol(e) : 0L; }();
-    if (env_chunk > 0) chunk_rows = std::min<int64_t>(pl.rows_pad, ceil_div64(env_chunk, 2 * BLOCK_M) * 2 * BLOCK_M);
-  }
-  static const int pairs_min_tiles = [] { const char* e = getenv("RBM_B200_PAIRS_MIN_TILES"); return e ? atoi(e) : 8; }();
-
-  // tensor maps: states are K-major A operands; W is read MN-major (v->h) and K-major (h->v)
-  CUtensorMap tm_w_mn, tm_w_k_single, tm_w_k_pair;
-  if ((rc = make_tmap(&tm_w_mn, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
-  // h->v reads W K-major in [n rows x 64] boxes: a CTA of a pair stages half of the 256 rows
-  if ((rc = make_tmap(&tm_w_k_single, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, (uint32_t)pl.bn_v))) return rc;
-  if ((rc = make_tmap(&tm_w_k_pair, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 128))) return rc;
-
-  // Few chains: one launch for all 2k half-steps (cluster per 128-chain row block, see umma_multistep_kernel)
-  bool ran_multistep = false;
-  {
-    const int nt_h = ceil_div(pl.nHp, pl.bn_h), nt_v = ceil_div(pl.nVp, pl.bn_v);
-    const int cs = std::max(nt_h, nt_v);
-    const int m_tiles = (int)(pl.rows_pad / BLOCK_M);
-    const int mode = multistep_mode();
-    const bool shape_ok = k >= 1 && pl.bn_h == pl.bn_v && multistep_cluster_ok(cs);
-    if (shape_ok && (mode == 1 || (mode == -1 && (int64_t)m_tiles * cs <= sm_count))) {
-      CUtensorMap tm[6];
-      if ((rc = make_tmap(&tm[0], Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
-      if ((rc = make_tmap(&tm[1], Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
-      tm[2] = tm_w_mn;
-      tm[3] = tm_w_k_single;
-      if ((rc = make_tmap(&tm[4], Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-      if ((rc = make_tmap(&tm[5], Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-      MultiArgs ma{};
-      ma.nbias[0] = nbh; ma.nbias[1] = nbv; ma.ldo[0] = pl.nHp; ma.ldo[1] = pl.nVp;
-      ma.n_valid[0] = pl.nH; ma.n_valid[1] = pl.nV; ma.n_tiles[0] = nt_h; ma.n_tiles[1] = nt_v;
-      ma.k_blocks[0] = pl.nVp / BLOCK_K; ma.k_blocks[1] = pl.nHp / BLOCK_K;
-      ma.steps = 2 * k; ma.first_dir = 0; ma.seed = seed; ma.chain_offset = chain_offset; ma.step_offset = step_offset;
-      ma.tag = TAG_GIBBS; ma.kf_magic = kKfMagic;
-      rc = pl.bn_h == 256 ? launch_multistep<256, EPI_GIBBS, EPI_GIBBS>(tm, ma, m_tiles, cs, st)
-                          : launch_multistep<128, EPI_GIBBS, EPI_GIBBS>(tm, ma, m_tiles, cs, st);
-      if (rc) return rc;
-      ran_multistep = true;
-    }
-  }
-
-  for (int64_t r0 = 0; !ran_multistep && r0 < pl.rows_pad; r0 += chunk_rows) {
-    const int64_t rows = std::min(chunk_rows, pl.rows_pad - r0);
-    __nv_bfloat16* Vc = Vs + r0 * pl.nVp;
-    __nv_bfloat16* Hc = Hs + r0 * pl.nHp;
+  if (chain_enabled() && k > 0) {
+    // all 2k half-steps in ONE dataflow launch (umma_chain.cuh)
+    uint32_t* flags = reinterpret_cast<uint32_t*>(base + pl.off_flags);
+    if ((rc = run_chain<EPI_GIBBS, EPI_GIBBS>(pl, Wp, Wlo, nbh, nbv, Vs, Hs, flags, 2 * k, seed, chain_offset, step_offset,
+                                              TAG_GIBBS, nullptr, nullptr, sm_count, st))) return rc;
+  } else if (k > 0) {
+    // round-1 path, kept for A/B measurements (RBM_B200_CHAIN=0): one launch per half-step
+    RBM_REQUIRE(Wlo == nullptr, RBM_B200_ERR_UNSUPPORTED, "split weights need the chain kernel (RBM_B200_CHAIN=0 is set)");
+    static const int pairs_min_tiles = env_int("RBM_B200_PAIRS_MIN_TILES", 8);
+    // tensor maps: states are K-major A operands; W is read MN-major (v->h) and K-major (h->v)
+    CUtensorMap tm_w_mn, tm_w_k_single, tm_w_k_pair;
+    if ((rc = make_tmap(&tm_w_mn, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
+    // h->v reads W K-major in [n rows x 64] boxes: a CTA of a pair stages half of the 256 rows
+    if ((rc = make_tmap(&tm_w_k_single, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, (uint32_t)pl.bn_v))) return rc;
+    if ((rc = make_tmap(&tm_w_k_pair, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 128))) return rc;
+    const int64_t rows = pl.rows_pad;
     // pairs pay off once every cluster loops over enough tiles (profiles/r01_pairs_vs_single.txt)
     const bool pairs = pairs_enabled() &&
                        (rows / (2 * BLOCK_M)) * ceil_div(std::max(pl.nVp, pl.nHp), 256) >= (int64_t)pairs_min_tiles * (sm_count / 2);
     CUtensorMap tm_v, tm_h, to_v, to_h;
-    if ((rc = make_tmap(&tm_v, Vc, (uint64_t)rows, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
-    if ((rc = make_tmap(&tm_h, Hc, (uint64_t)rows, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
+    if ((rc = make_tmap(&tm_v, Vs, (uint64_t)rows, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
+    if ((rc = make_tmap(&tm_h, Hs, (uint64_t)rows, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
     // epilogue stores: [32 chains x 32 units] boxes, 64-byte swizzle
-    if ((rc = make_tmap(&to_v, Vc, (uint64_t)rows, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    if ((rc = make_tmap(&to_h, Hc, (uint64_t)rows, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_tmap(&to_v, Vs, (uint64_t)rows, (uint64_t)pl.nVp, (uint64_t)pl.nVp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_tmap(&to_h, Hs, (uint64_t)rows, (uint64_t)pl.nHp, (uint64_t)pl.nHp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     const CUtensorMap& tm_w_k = (pairs && pl.bn_v == 256) ? tm_w_k_pair : tm_w_k_single;
 
     HalfStepArgs ah{}, av{};
-    ah.out = Hc; ah.nbias = nbh; ah.ldo = pl.nHp; ah.m_tiles = (int)(rows / BLOCK_M);
-    ah.n_tiles = ceil_div(pl.nHp, pl.bn_h); ah.k_blocks = pl.nVp / BLOCK_K; ah.chain_offset = chain_offset + (uint64_t)r0; ah.n_valid = pl.nH;
-    av.out = Vc; av.nbias = nbv; av.ldo = pl.nVp; av.m_tiles = ah.m_tiles;
-    av.n_tiles = ceil_div(pl.nVp, pl.bn_v); av.k_blocks = pl.nHp / BLOCK_K; av.chain_offset = chain_offset + (uint64_t)r0; av.n_valid = pl.nV;
+    ah.out = Hs; ah.nbias = nbh; ah.ldo = pl.nHp; ah.m_tiles = (int)(rows / BLOCK_M);
+    ah.n_tiles = ceil_div(pl.nHp, pl.bn_h); ah.k_blocks = pl.nVp / BLOCK_K; ah.chain_offset = chain_offset; ah.n_valid = pl.nH;
+    av.out = Vs; av.nbias = nbv; av.ldo = pl.nVp; av.m_tiles = ah.m_tiles;
+    av.n_tiles = ceil_div(pl.nVp, pl.bn_v); av.k_blocks = pl.nHp / BLOCK_K; av.chain_offset = chain_offset; av.n_valid = pl.nV;
 
     for (int s = 0; s < k; ++s) {
       ah.ctx = make_draw_ctx(seed, step_offset + 2ull * s, TAG_GIBBS);
@@ -733,7 +593,7 @@ size_t umma_ais_workspace_bytes(int nV, int nH, int64_t M) { return make_plan(nV
 // increment sum_j softplus(b_k x_j) - softplus(b_{k-1} x_j) and the draw h ~ sigma(b_k x);
 // then v ~ sigma(a + b_k h W^T).  logw[b] (nats) is written for this shard's chains.
 int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n_betas, uint64_t seed,
-                 uint64_t chain_offset, double* logw, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 uint64_t chain_offset, double* logw, void* ws, size_t ws_bytes, cudaStream_t st, bool split_w) {
   const Plan pl = make_plan(p->n_visible, p->n_hidden, M);
   RBM_REQUIRE(ws != nullptr && ws_bytes >= pl.total, RBM_B200_ERR_WORKSPACE,
               "AIS needs %zu bytes of workspace, got %zu", pl.total, ws_bytes);
@@ -744,9 +604,13 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
   }
   const int sm_count = di.sm_count, cc_major = di.cc_major;
   RBM_REQUIRE(cc_major == 10, RBM_B200_ERR_NO_DEVICE, "AIS needs an sm_100 device (got cc %d.x)", cc_major);
+  const bool use_chain = chain_enabled() && n_betas <= kMaxDeviceBetas;
+  RBM_REQUIRE(!split_w || use_chain, RBM_B200_ERR_UNSUPPORTED,
+              "AIS with split weights needs the chain kernel (at most %d betas)", kMaxDeviceBetas);
 
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   uint16_t* Wp = reinterpret_cast<uint16_t*>(base + pl.off_W);
+  uint16_t* Wlo = split_w ? reinterpret_cast<uint16_t*>(base + pl.off_Wlo) : nullptr;
   float* nbh = reinterpret_cast<float*>(base + pl.off_nbh);
   float* nbv = reinterpret_cast<float*>(base + pl.off_nbv);
   __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(base + pl.off_V);
@@ -755,7 +619,11 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
 
   {
     const int64_t n = (int64_t)pl.nVp * pl.nHp;
-    pad_w_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W_bf16, Wp, pl.nV, pl.nH, pl.nVp, pl.nHp);
+    if (split_w)
+      pad_w_split_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W, reinterpret_cast<__nv_bfloat16*>(Wp),
+                                                                      reinterpret_cast<__nv_bfloat16*>(Wlo), pl.nV, pl.nH, pl.nVp, pl.nHp);
+    else
+      pad_w_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W_bf16, Wp, pl.nV, pl.nH, pl.nVp, pl.nHp);
     const int nh256 = round_up(pl.nHp, 256), nv256 = round_up(pl.nVp, 256);
     nbias_kernel<<<ceil_div(nh256, 256), 256, 0, st>>>(p->hbias, nbh, pl.nH, nh256);
     nbias_kernel<<<ceil_div(nv256, 256), 256, 0, st>>>(p->vbias, nbv, pl.nV, nv256);
@@ -766,7 +634,24 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
   }
   int rc = check_launch("ais staging kernels");
   if (rc) return rc;
+  const int K = n_betas - 1;
 
+  if (use_chain) {
+    // the whole schedule in ONE dataflow launch: K hidden steps, K-1 visible steps (the last transition cannot
+    // change the estimate); half-step counter 2k / 2k+1, beta index 1 + t/2
+    float* betas_dev = reinterpret_cast<float*>(base + pl.off_betas);
+    std::vector<float> bf(n_betas);
+    for (int i = 0; i < n_betas; ++i) bf[i] = (float)betas[i];
+    // pageable source: the runtime stages the copy before returning, so `bf` may go out of scope
+    RBM_CUDA_TRY(cudaMemcpyAsync(betas_dev, bf.data(), sizeof(float) * (size_t)n_betas, cudaMemcpyHostToDevice, st));
+    uint32_t* flags = reinterpret_cast<uint32_t*>(base + pl.off_flags);
+    if ((rc = run_chain<EPI_AIS_WEIGHT, EPI_ANNEALED>(pl, Wp, Wlo, nbh, nbv, Vs, Hs, flags, 2 * K - 1, seed, chain_offset, 2,
+                                                      TAG_AIS, betas_dev, wpart, sm_count, st))) return rc;
+    ais_reduce_kernel<<<(unsigned)ceil_div64(M, 256), 256, 0, st>>>(wpart, pl.wpart_ld, M, logw);
+    return check_launch("ais_reduce_kernel");
+  }
+
+  // one launch per half-step (schedules longer than kMaxDeviceBetas, or RBM_B200_CHAIN=0)
   CUtensorMap tm_v, tm_h, tm_w_mn, tm_w_k;
   if ((rc = make_tmap(&tm_v, Vs, (uint64_t)pl.rows_pad, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_M))) return rc;
   if ((rc = make_tmap(&tm_h, Hs, (uint64_t)pl.rows_pad, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_M))) return rc;
@@ -789,36 +674,6 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
   av.n_tiles = ceil_div(pl.nVp, pl.bn_v); av.k_blocks = pl.nHp / BLOCK_K; av.chain_offset = chain_offset;
   av.n_valid = pl.nV; av.wpart = wpart; av.wpart_ld = pl.wpart_ld;
 
-  const int K = n_betas - 1;
-  // Few chains per GPU (e.g. config 5 sharded over 8 GPUs: 2048 chains): the whole schedule in ONE launch
-  {
-    const int nt_h = ceil_div(pl.nHp, pl.bn_h), nt_v = ceil_div(pl.nVp, pl.bn_v);
-    const int cs = std::max(nt_h, nt_v);
-    const int m_tiles = (int)(pl.rows_pad / BLOCK_M);
-    const int mode = multistep_mode();
-    const bool shape_ok = pl.bn_h == pl.bn_v && multistep_cluster_ok(cs) && n_betas <= kMaxDeviceBetas && !pairs;
-    if (shape_ok && (mode == 1 || (mode == -1 && (int64_t)m_tiles * cs <= sm_count))) {
-      float* betas_dev = reinterpret_cast<float*>(base + pl.off_betas);
-      std::vector<float> bf(n_betas);
-      for (int i = 0; i < n_betas; ++i) bf[i] = (float)betas[i];
-      // pageable source: the runtime stages the copy before returning, so `bf` may go out of scope
-      RBM_CUDA_TRY(cudaMemcpyAsync(betas_dev, bf.data(), sizeof(float) * (size_t)n_betas, cudaMemcpyHostToDevice, st));
-      CUtensorMap tm[6];
-      tm[0] = tm_v; tm[1] = tm_h; tm[2] = tm_w_mn; tm[3] = tm_w_k; tm[4] = to_h; tm[5] = to_v;
-      MultiArgs ma{};
-      ma.nbias[0] = nbh; ma.nbias[1] = nbv; ma.ldo[0] = pl.nHp; ma.ldo[1] = pl.nVp;
-      ma.n_valid[0] = pl.nH; ma.n_valid[1] = pl.nV; ma.n_tiles[0] = nt_h; ma.n_tiles[1] = nt_v;
-      ma.k_blocks[0] = pl.nVp / BLOCK_K; ma.k_blocks[1] = pl.nHp / BLOCK_K;
-      ma.steps = 2 * K - 1;            // K hidden steps, K-1 visible steps (the last transition is skipped)
-      ma.first_dir = 0; ma.seed = seed; ma.chain_offset = chain_offset; ma.step_offset = 2;   // half-step counter 2k / 2k+1
-      ma.tag = TAG_AIS; ma.kf_magic = kKfMagic; ma.betas = betas_dev; ma.wpart = wpart; ma.wpart_ld = pl.wpart_ld;
-      rc = pl.bn_h == 256 ? launch_multistep<256, EPI_AIS_WEIGHT, EPI_ANNEALED>(tm, ma, m_tiles, cs, st)
-                          : launch_multistep<128, EPI_AIS_WEIGHT, EPI_ANNEALED>(tm, ma, m_tiles, cs, st);
-      if (rc) return rc;
-      ais_reduce_kernel<<<(unsigned)ceil_div64(M, 256), 256, 0, st>>>(wpart, pl.wpart_ld, M, logw);
-      return check_launch("ais_reduce_kernel");
-    }
-  }
   for (int k = 1; k <= K; ++k) {
     const float bk = (float)betas[k], bkm1 = (float)betas[k - 1];
     ah.ctx = make_draw_ctx(seed, 2ull * k, TAG_AIS);

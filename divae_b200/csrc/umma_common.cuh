@@ -175,7 +175,7 @@ struct SmemLayout {
 #ifndef RBM_PAIR_STAGES
 #define RBM_PAIR_STAGES 5
 #endif
-  static constexpr int kStages = CTAS == 2 ? RBM_PAIR_STAGES : 4;
+  static constexpr int kStages = CTAS == 2 ? RBM_PAIR_STAGES : (BLOCK_N >= 256 ? 4 : BLOCK_N == 128 ? 6 : 8);
   static constexpr int kBBytes = (BLOCK_N / CTAS) * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStoreOffset = kStages * kStageBytes;             // epilogue -> TMA-store staging
@@ -279,12 +279,24 @@ struct EpiParams {
 // Epilogue of ONE 128 x BLOCK_N tile for one warp: TMEM -> decisions -> swizzled smem box -> TMA store.
 //   tmem_acc   TMEM address of the accumulator stage (column 0 of the tile, lane 0)
 //   wait_full  blocks until the MMA has completed the accumulator;  release  hands the stage back
+// Column sets that take part in a BLOCK_N-wide tile: every set needs at least one 32-unit Philox group, so
+// tiles narrower than 32 * kEpiSets columns leave the surplus epilogue warps idle (they skip the tile).
+template <int BLOCK_N>
+struct EpiSplit {
+  static constexpr int kSets = (BLOCK_N / 32 < kEpiSets) ? BLOCK_N / 32 : kEpiSets;
+  static constexpr int kWarps = 4 * kSets;            // epilogue warps that work on (and arrive for) a tile
+  static constexpr int kColsPerWarp = BLOCK_N / kSets;
+};
+
+//   wrow       EPI_AIS_WEIGHT: this chain's log-weight slots, one per 32-unit group of hidden units (log2 units);
+//              the group's sum is ADDED with one red per thread, so the result does not depend on the tiling
 template <int BLOCK_N, int EPI, class WaitFn, class ReleaseFn>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtensorMap* tmap_out, uint32_t tmem_acc,
                                               int n_blk, int row_base, uint32_t chain, int quarter, int cq, int lane,
-                                              uint32_t stage_warp, float& wsum, WaitFn wait_full, ReleaseFn release) {
-  constexpr int kColsPerWarp = BLOCK_N / kEpiSets;
+                                              uint32_t stage_warp, float* wrow, WaitFn wait_full, ReleaseFn release) {
+  constexpr int kColsPerWarp = EpiSplit<BLOCK_N>::kColsPerWarp;
   constexpr int kGroups = kColsPerWarp / 32;   // 32-unit Philox groups per warp per tile
+  float wsum = 0.f;
   // staging box of this warp: row `lane` = 64 B, 16-B chunk c stored at c ^ ((lane >> 1) & 3)  (SWIZZLE_64B)
   const uint32_t stage_row = stage_warp + (uint32_t)lane * 64u;
   const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
@@ -389,6 +401,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
           tma_store_2d(tmap_out, stage_warp, col0, row_base);
           tma_store_commit();
         }
+      }
+      if (EPI == EPI_AIS_WEIGHT && live) {
+        atomicAdd(wrow + (col0 >> 5), wsum);   // one owner per (chain, group) and half-step: the order of adds is fixed
+        wsum = 0.f;
       }
       if (g + 1 < kGroups) draw_group(g + 1);
     }
@@ -672,7 +688,6 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const int row_base = (m_blk * CTAS + (int)cta_rank) * BLOCK_M + quarter * 32;
       const int row = row_base + lane;
       const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)row);
-      float wsum = 0.f;   // EPI_AIS_WEIGHT: this thread's log-weight increment over its columns (log2 units)
       EpiParams ep;
       ep.nbias = args.nbias; ep.ldo = args.ldo; ep.n_valid = args.n_valid; ep.ctx = args.ctx;
       ep.scale = args.scale; ep.bmul = args.bmul; ep.ratio = args.ratio; ep.debug_mode = args.debug_mode;
@@ -689,12 +704,8 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                            cq, lane, stage_warp, wait_full, release);
       else
         epilogue_tile<BLOCK_N, EPI>(ep, &tmap_out, tmem_base + (uint32_t)(as * BLOCK_N), n_blk, row_base, chain, quarter,
-                                    cq, lane, stage_warp, wsum, wait_full, release);
-      if (EPI == EPI_AIS_WEIGHT) {
-        // exactly one thread owns (row, slot) in a launch: plain read-modify-write, deterministic
-        float* slot_ptr = args.wpart + (size_t)row * args.wpart_ld + (n_blk * kEpiSets + cq);
-        *slot_ptr += wsum;
-      }
+                                    cq, lane, stage_warp, EPI == EPI_AIS_WEIGHT ? args.wpart + (size_t)row * args.wpart_ld : nullptr,
+                                    wait_full, release);
     }
     if (lane == 0) tma_store_wait_all();   // state tiles must be complete before the kernel ends
   }

@@ -46,7 +46,7 @@ size_t umma_workspace_bytes(int nV, int nH, int64_t B);
 int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains,
                      uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws,
                      size_t ws_bytes, cudaStream_t st, float* S_vh = nullptr, float* S_v = nullptr,
-                     float* S_h = nullptr);
+                     float* S_h = nullptr, bool split_w = false);
 
 // decoder MLP on generated samples: one tcgen05 GEMM per layer, split-bf16 operands
 size_t umma_decoder_workspace_bytes(const rbm_b200_decoder* d, int64_t B);
@@ -60,6 +60,6 @@ int gumbel_smooth(float* logits, float* samples, int64_t B, int n, float beta, i
 
 size_t umma_ais_workspace_bytes(int nV, int nH, int64_t M);
 int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n_betas, uint64_t seed,
-                 uint64_t chain_offset, double* logw, void* ws, size_t ws_bytes, cudaStream_t st);
+                 uint64_t chain_offset, double* logw, void* ws, size_t ws_bytes, cudaStream_t st, bool split_w = false);
 
 }  // namespace rbm

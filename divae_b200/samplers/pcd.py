@@ -78,7 +78,7 @@ class PCD(BaseSampler):
         if rbm is None or rbm is not self._modules.get("_RBM"):      # the submodule was replaced after construction
             rbm = self.__dict__["_rbm_plain"] = self._RBM
         B = self._batch_size
-        need_bf16 = self._variant != _lib.VARIANT_GENERAL
+        need_bf16 = self._variant not in (_lib.VARIANT_GENERAL, _lib.VARIANT_UMMA_SPLIT)
         p, keep = self._pack.pack(rbm, need_bf16=need_bf16)     # raises for CPU parameters (no CPU fallback)
         dev = keep[0].device
         nV, nH = p.n_visible, p.n_hidden

@@ -57,7 +57,10 @@ enum {
   RBM_B200_VARIANT_AUTO = 0,
   RBM_B200_VARIANT_GENERAL = 1, /* fp32 SIMT, one launch per half-step, any shape, fp32 W */
   RBM_B200_VARIANT_SMEM = 2,    /* persistent: W (bf16) resident in shared memory, states on chip */
-  RBM_B200_VARIANT_UMMA = 3     /* tcgen05/TMEM GEMM per half-step fed by TMA, bf16 {0,1} state tiles */
+  RBM_B200_VARIANT_UMMA = 3,    /* tcgen05/TMEM GEMM per half-step fed by TMA, bf16 {0,1} state tiles */
+  RBM_B200_VARIANT_UMMA_SPLIT = 4 /* UMMA with W carried as bf16 high + bf16 low parts (needs the fp32 W): the GEMM
+                                     runs over a doubled K axis and the pre-activations are fp32-grade (~2^-17
+                                     relative) instead of bf16-rounded-W grade (2^-9); about twice the tensor time */
 };
 
 /* Epilogue mode of a single half-step. */
@@ -201,7 +204,11 @@ RBM_B200_API int rbm_b200_cd_step(float *W, float *vbias, float *hbias, float *d
  *   betas   HOST pointer, n_betas doubles, betas[0] = 0 < ... < betas[n_betas-1] = 1.
  *   logw    DEVICE pointer, n_chains doubles (nats), overwritten.
  *   chain_offset  global id of this shard's first chain (draws are keyed by global id).
- * Needs W_bf16 and rbm_b200_ais_workspace(...) bytes of workspace. */
+ * Needs rbm_b200_ais_workspace(...) bytes of workspace and either W_bf16 (W rounded to bf16) or, with
+ * W_bf16 == NULL, the fp32 W, which is then carried as bf16 high + low parts (fp32-grade
+ * pre-activations at about twice the tensor time; see RBM_B200_VARIANT_UMMA_SPLIT).
+ * The whole schedule runs as ONE persistent launch (up to 2^18 betas; longer schedules fall back to
+ * one launch per half-step, W_bf16 only). */
 RBM_B200_API size_t rbm_b200_ais_workspace(int32_t n_visible, int32_t n_hidden, int64_t n_chains);
 RBM_B200_API int rbm_b200_ais_run(const rbm_b200_params *p, int64_t n_chains, const double *betas,
                                   int32_t n_betas, uint64_t seed, uint64_t chain_offset, double *logw,
