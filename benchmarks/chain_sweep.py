@@ -56,13 +56,27 @@ def main():
         "bn128": {"RBM_B200_CHAIN_BN": "128"},
         "bn64": {"RBM_B200_CHAIN_BN": "64"},
         "auto": {},
+        "sb8k": {"RBM_B200_CHAIN_SB": "8192"},
+        "sb16k": {"RBM_B200_CHAIN_SB": "16384"},
+        "sb32k": {"RBM_B200_CHAIN_SB": "32768"},
+        "sb1": {"RBM_B200_CHAIN_SB": "-1"},
+        "opts0": {"RBM_B200_CHAIN_OPTS": "0"},
+        "opts1": {"RBM_B200_CHAIN_OPTS": "1"},
+        "opts4": {"RBM_B200_CHAIN_OPTS": "4"},
+        "opts5": {"RBM_B200_CHAIN_OPTS": "5"},
+        "opts6": {"RBM_B200_CHAIN_OPTS": "6"},
+        "opts7": {"RBM_B200_CHAIN_OPTS": "7"},
+        "grid64": {"RBM_B200_CHAIN_GRID": "64"},
+        "grid70": {"RBM_B200_CHAIN_GRID": "70"},
     }
     out = open(args.out, "a") if args.out else None
     for B in [int(x) for x in args.chains.split(",")]:
         for name in args.configs.split(","):
             env = dict(os.environ)
-            for key in ("RBM_B200_CHAIN", "RBM_B200_CHAIN_BN", "RBM_B200_CHAIN_PAIRS"):
+            for key in ("RBM_B200_CHAIN", "RBM_B200_CHAIN_BN", "RBM_B200_CHAIN_PAIRS", "RBM_B200_CHAIN_SB", "RBM_B200_CHAIN_GRID", "RBM_B200_CHAIN_OPTS"):
                 env.pop(key, None)
+            if name.startswith("opts") and name not in envs:
+                envs[name] = {"RBM_B200_CHAIN_OPTS": name[4:]}
             env.update(envs[name])
             code = WORKER % dict(root=ROOT, n=args.n, B=B, k=args.k, reps=args.reps, variant=args.variant)
             try:

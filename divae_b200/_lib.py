@@ -63,6 +63,7 @@ PROTOTYPES = {
     "rbm_b200_half_step": (_int, [_P, _int, _vp, _vp, _i64, _int, _vp, _u64, _u64, _u64, _vp]),
     "rbm_b200_init_chains": (_int, [_vp, _i64, _i32, _u64, _u64, _u64, _vp]),
     "rbm_b200_block_gibbs_workspace": (_sz, [_i32, _i32, _i64, _int]),
+    "rbm_b200_block_gibbs_launch_count": (_i64, [_i32, _i32, _i64, _i32, _int]),
     "rbm_b200_block_gibbs": (_int, [_P, _vp, _vp, _i64, _i32, _int, _u64, _u64, _u64, _int, _vp, _sz, _vp]),
     "rbm_b200_block_gibbs_stats": (_int, [_P, _vp, _vp, _i64, _i32, _int, _u64, _u64, _u64, _int, _vp, _sz, _f32, _vp, _vp,
                                            _vp, _vp, _vp]),
@@ -76,6 +77,7 @@ PROTOTYPES = {
                                  _vp, _vp, _sz, _vp]),
     "rbm_b200_ais_workspace": (_sz, [_i32, _i32, _i64]),
     "rbm_b200_ais_run": (_int, [_P, _i64, ctypes.POINTER(ctypes.c_double), _i32, _u64, _u64, _vp, _vp, _sz, _vp]),
+    "rbm_b200_ais_run_ex": (_int, [_P, _i64, ctypes.POINTER(ctypes.c_double), _i32, _u64, _u64, _vp, _int, _vp, _sz, _vp]),
     "rbm_b200_decoder_workspace": (_sz, [_D, _i64]),
     "rbm_b200_decoder_forward": (_int, [_D, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _u64, _int, _vp, _sz, _vp]),
     "rbm_b200_gumbel_smooth": (_int, [_vp, _vp, _i64, _i32, _f32, _int, _int, _u64, _u64, _u64, ctypes.c_uint32, _vp]),
@@ -93,11 +95,18 @@ def load(build_if_missing=True):
     with _lock:
         if _lib is not None:
             return _lib
+        from . import build as _build
         if not os.path.isfile(LIB_PATH):
             if not build_if_missing:
                 raise RuntimeError("librbm_b200.so is missing (%s); run `python -m divae_b200.build`" % LIB_PATH)
-            from . import build as _build
             _build.build()
+        elif _build.needs_build():
+            # the sources or the header changed after the binary was built: same prototypes, different kernels
+            if build_if_missing and _build.have_nvcc():
+                _build.build()
+            elif os.environ.get("RBM_B200_ALLOW_STALE") != "1":
+                raise RuntimeError("librbm_b200.so is older than divae_b200/csrc or include/ (source digest mismatch); "
+                                   "run `python -m divae_b200.build` (RBM_B200_ALLOW_STALE=1 loads it anyway)")
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)  # AttributeError if the ABI is incomplete: fail loudly

@@ -32,15 +32,14 @@ def _f32c(t, name):
 
 
 class ParamPack:
-    """Device views of (W, a, c) plus a cached bf16 copy of W, refreshed when W changes.
+    """Device views of (W, a, c) as the C struct the library takes.
 
-    The packed struct is cached and re-used while the parameter tensors are the same objects at the
-    same version (an optimiser step bumps `_version`), so the per-call host cost is three integer
-    compares."""
+    Only the fp32 parameters are handed over: the bf16 kernels round W inside the library on every call
+    (rbm_b200_params.W_bf16 = NULL), so in-place writes that do not bump `_version` (`p.data.copy_()`, legacy
+    optimisers) can never leave a stale low-precision copy behind.  The packed struct itself only holds pointers
+    and shapes; it is cached while the parameter tensors are the same objects at the same addresses."""
 
     def __init__(self):
-        self._bf16 = None
-        self._key = None
         self._packed = None
         self._packed_key = None
 
@@ -54,30 +53,24 @@ class ParamPack:
     def __deepcopy__(self, memo):
         return ParamPack()
 
-    def pack(self, rbm, need_bf16):
+    def pack(self, rbm, need_bf16=False):
         # nn.Module attribute access goes through __getattr__ (slow): read the parameter dict directly when there is one
         params = rbm.__dict__.get("_parameters") if hasattr(rbm, "__dict__") else None
         if params is not None and "_weights" in params:
             Wp, ap, cp = params["_weights"], params["_visible_bias"], params["_hidden_bias"]
         else:
             Wp, ap, cp = rbm.weights, rbm.visible_bias, rbm.hidden_bias
-        pkey = (id(Wp), Wp._version, id(ap), ap._version, id(cp), cp._version, Wp.data_ptr(), need_bf16)
+        pkey = (id(Wp), Wp.data_ptr(), id(ap), ap.data_ptr(), id(cp), cp.data_ptr(), Wp.dtype, Wp.is_contiguous())
         if pkey == self._packed_key:
             return self._packed
         W = _f32c(Wp.detach(), "RBM weights")
         a = _f32c(ap.detach(), "RBM visible bias")
         c = _f32c(cp.detach(), "RBM hidden bias")
-        wb = None
-        if need_bf16:
-            key = (W.data_ptr(), Wp._version, W.device)
-            if self._key != key or self._bf16 is None:
-                self._bf16 = W.to(torch.bfloat16)  # round-to-nearest-even
-                self._key = key
-            wb = self._bf16
-        p = _lib.RbmParams(W.shape[0], W.shape[1], W.data_ptr(), wb.data_ptr() if wb is not None else 0,
-                           a.data_ptr(), c.data_ptr())
-        self._packed = (p, (W, a, c, wb))  # keep tensors alive for the duration of the call
-        self._packed_key = pkey
+        p = _lib.RbmParams(W.shape[0], W.shape[1], W.data_ptr(), 0, a.data_ptr(), c.data_ptr())
+        self._packed = (p, (W, a, c))  # keep tensors alive for the duration of the call
+        # non-fp32 / non-contiguous parameters are converted copies: never cache those
+        direct = W.data_ptr() == Wp.data_ptr() and a.data_ptr() == ap.data_ptr() and c.data_ptr() == cp.data_ptr()
+        self._packed_key = pkey if direct else None
         return self._packed
 
 

@@ -29,6 +29,17 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def have_nvcc():
+    try:
+        nv = _nvcc()
+    except RuntimeError:
+        return False
+    if nv == "nvcc":
+        import shutil
+        return shutil.which("nvcc") is not None
+    return True
+
+
 def _digest():
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(HERE, "..", "include")):

@@ -87,10 +87,10 @@ int pick_variant(const rbm_b200_params* p, int64_t B, int variant) {
   if (variant == RBM_B200_VARIANT_UMMA_SPLIT) return RBM_B200_VARIANT_UMMA;
   if (variant != RBM_B200_VARIANT_AUTO) return variant;
   const int nmax = p->n_visible > p->n_hidden ? p->n_visible : p->n_hidden;
-  if (p->W_bf16 && smem_variant_supported(p->n_visible, p->n_hidden) && (nmax <= 128 || B < 8192))
-    return RBM_B200_VARIANT_SMEM;
-  if (p->W_bf16 && umma_variant_supported(p->n_visible, p->n_hidden) && B >= 128) return RBM_B200_VARIANT_UMMA;
-  if (p->W_bf16 && smem_variant_supported(p->n_visible, p->n_hidden)) return RBM_B200_VARIANT_SMEM;
+  // (the bf16 kernels round the fp32 W themselves when no bf16 copy is handed in)
+  if (smem_variant_supported(p->n_visible, p->n_hidden) && (nmax <= 128 || B < 8192)) return RBM_B200_VARIANT_SMEM;
+  if (umma_variant_supported(p->n_visible, p->n_hidden) && B >= 128) return RBM_B200_VARIANT_UMMA;
+  if (smem_variant_supported(p->n_visible, p->n_hidden)) return RBM_B200_VARIANT_SMEM;
   return RBM_B200_VARIANT_GENERAL;
 }
 
@@ -146,11 +146,23 @@ int rbm_b200_init_chains(float* v, int64_t B, int32_t n_visible, uint64_t seed, 
 size_t rbm_b200_block_gibbs_workspace(int32_t n_visible, int32_t n_hidden, int64_t B, int variant) {
   if (B <= 0) return 0;
   rbm_b200_params q{};
-  q.n_visible = n_visible; q.n_hidden = n_hidden; q.W_bf16 = (const uint16_t*)1;
+  q.n_visible = n_visible; q.n_hidden = n_hidden;
   switch (pick_variant(&q, B, variant)) {
     case RBM_B200_VARIANT_UMMA: return umma_workspace_bytes(n_visible, n_hidden, B);
     case RBM_B200_VARIANT_SMEM: return smem_workspace_bytes(n_visible, n_hidden, B);
     default: return 0;
+  }
+}
+
+int64_t rbm_b200_block_gibbs_launch_count(int32_t n_visible, int32_t n_hidden, int64_t B, int32_t k, int variant) {
+  if (B <= 0 || n_visible <= 0 || n_hidden <= 0 || k < 0) return 0;
+  if (require_device()) return -1;
+  rbm_b200_params q{};
+  q.n_visible = n_visible; q.n_hidden = n_hidden;
+  switch (pick_variant(&q, B, variant)) {
+    case RBM_B200_VARIANT_UMMA: return umma_launch_count(n_visible, n_hidden, B, k, variant == RBM_B200_VARIANT_UMMA_SPLIT);
+    case RBM_B200_VARIANT_SMEM: return 1;              // one persistent kernel: staging, 2k half-steps, outputs
+    default: return 1 + 2 * (int64_t)k;                // GENERAL: initial state + one kernel per half-step
   }
 }
 
@@ -170,7 +182,7 @@ static int block_gibbs_impl(const rbm_b200_params* p, float* v, float* h, int64_
   if (B == 0) return 0;
   const int chosen = pick_variant(p, B, variant);
   if (chosen == RBM_B200_VARIANT_SMEM) {
-    RBM_REQUIRE(p->W_bf16, RBM_B200_ERR_INVALID, "SMEM variant needs W_bf16");
+    RBM_REQUIRE(p->W_bf16 || p->W, RBM_B200_ERR_INVALID, "SMEM variant needs W (fp32) or W_bf16");
     const bool fuse = S_vh != nullptr && k > 0 && smem_can_fuse_stats(p->n_visible, p->n_hidden);
     if (stats_fused) *stats_fused = fuse;
     return smem_block_gibbs(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, workspace,
@@ -179,7 +191,7 @@ static int block_gibbs_impl(const rbm_b200_params* p, float* v, float* h, int64_
   if (chosen == RBM_B200_VARIANT_UMMA) {
     const bool split = variant == RBM_B200_VARIANT_UMMA_SPLIT;
     if (split) RBM_REQUIRE(p->W, RBM_B200_ERR_INVALID, "UMMA_SPLIT variant needs the fp32 W");
-    else RBM_REQUIRE(p->W_bf16, RBM_B200_ERR_INVALID, "UMMA variant needs W_bf16");
+    else RBM_REQUIRE(p->W_bf16 || p->W, RBM_B200_ERR_INVALID, "UMMA variant needs W (fp32) or W_bf16");
     const bool fuse = S_vh != nullptr && k > 0;
     if (stats_fused) *stats_fused = fuse;
     return umma_block_gibbs(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, workspace,
@@ -328,6 +340,28 @@ int rbm_b200_ais_run(const rbm_b200_params* p, int64_t n_chains, const double* b
   // W_bf16 == NULL: the fp32 W is carried as bf16 high + low parts (fp32-grade pre-activations, K axis doubled)
   return umma_ais_run(p, n_chains, betas, n_betas, seed, chain_offset, logw, workspace, workspace_bytes,
                       (cudaStream_t)stream, p->W_bf16 == nullptr);
+}
+
+int rbm_b200_ais_run_ex(const rbm_b200_params* p, int64_t n_chains, const double* betas, int32_t n_betas,
+                        uint64_t seed, uint64_t chain_offset, double* logw, int variant, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  int rc = check_params(p, false);
+  if (rc) return rc;
+  RBM_REQUIRE(variant == RBM_B200_VARIANT_AUTO || variant == RBM_B200_VARIANT_UMMA || variant == RBM_B200_VARIANT_UMMA_SPLIT,
+              RBM_B200_ERR_INVALID, "AIS runs on the UMMA kernels: variant must be AUTO, UMMA or UMMA_SPLIT (got %d)", variant);
+  const bool split = variant == RBM_B200_VARIANT_UMMA_SPLIT;
+  if (split) RBM_REQUIRE(p->W != nullptr, RBM_B200_ERR_INVALID, "split weights need the fp32 W");
+  else RBM_REQUIRE(p->W_bf16 != nullptr || p->W != nullptr, RBM_B200_ERR_INVALID, "AIS needs W (fp32) or W_bf16");
+  RBM_REQUIRE(n_chains >= 0, RBM_B200_ERR_INVALID, "negative chain count");
+  RBM_REQUIRE(betas != nullptr && n_betas >= 2, RBM_B200_ERR_INVALID, "need at least two betas");
+  RBM_REQUIRE(betas[0] == 0.0 && betas[n_betas - 1] == 1.0, RBM_B200_ERR_INVALID, "betas must run from 0 to 1");
+  for (int i = 1; i < n_betas; ++i)
+    RBM_REQUIRE(betas[i] > betas[i - 1], RBM_B200_ERR_INVALID, "betas must be strictly increasing");
+  if (n_chains == 0) return 0;
+  RBM_REQUIRE(logw != nullptr, RBM_B200_ERR_INVALID, "logw is NULL");
+  if ((rc = require_device())) return rc;
+  return umma_ais_run(p, n_chains, betas, n_betas, seed, chain_offset, logw, workspace, workspace_bytes,
+                      (cudaStream_t)stream, split);
 }
 
 size_t rbm_b200_decoder_workspace(const rbm_b200_decoder* d, int64_t B) {

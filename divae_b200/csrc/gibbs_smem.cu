@@ -32,7 +32,8 @@ constexpr int kSlots = 2 * kMaxWords;       // state slots per side: words, or h
 constexpr float kNegLog2e = -1.4426950408889634f;
 
 struct SmemArgs {
-  const uint16_t* W;     // [nV, nH] bf16 row-major (global)
+  const uint16_t* W;     // [nV, nH] bf16 row-major (global), or nullptr: W32 is rounded to bf16 (RNE) while staging
+  const float* W32;      // [nV, nH] fp32 row-major (global)
   const float* vbias;
   const float* hbias;
   float* v;              // [B, nV] fp32 in/out
@@ -237,7 +238,29 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
 
   const int tid = threadIdx.x;
   // ---- stage W (zero padded) and the pre-scaled biases once per CTA
-  if ((nH & 7) == 0 && (reinterpret_cast<uintptr_t>(args.W) & 15) == 0) {
+  if (args.W == nullptr) {
+    // fp32 parameters, rounded here: the sampler never sees a bf16 copy that could be stale
+    if ((nH & 3) == 0 && (reinterpret_cast<uintptr_t>(args.W32) & 15) == 0) {
+      const int chunks = nH >> 2;                     // float4 chunks per row
+      for (int idx = tid; idx < nV * chunks; idx += blockDim.x) {
+        const int i = idx / chunks, c4 = idx % chunks;
+        const float4 w = __ldg(reinterpret_cast<const float4*>(args.W32 + (size_t)i * nH) + c4);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(Ws + (size_t)i * ldw + 4 * c4) = pk;
+      }
+      const int padc = ldw - nH;
+      for (int idx = tid; idx < nV * padc; idx += blockDim.x)
+        reinterpret_cast<uint16_t*>(Ws)[(idx / padc) * ldw + nH + idx % padc] = 0;
+      for (int idx = tid + nV * ldw; idx < nVp * ldw; idx += blockDim.x) reinterpret_cast<uint16_t*>(Ws)[idx] = 0;
+    } else {
+      for (int idx = tid; idx < nVp * ldw; idx += blockDim.x) {
+        const int i = idx / ldw, j = idx % ldw;
+        Ws[idx] = __float2bfloat16_rn((i < nV && j < nH) ? args.W32[(size_t)i * nH + j] : 0.f);
+      }
+    }
+  } else if ((nH & 7) == 0 && (reinterpret_cast<uintptr_t>(args.W) & 15) == 0) {
     const int chunks = nH >> 3;                       // 16-byte chunks per row
     // asynchronous 16-byte copies global -> shared (LDGSTS): all of a thread's copies are in flight at once
     for (int idx = tid; idx < nV * chunks; idx += blockDim.x) {
@@ -472,7 +495,7 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   if (rc_di) return rc_di;
   const int sm_count = di.sm_count;
   SmemArgs a{};
-  a.W = p->W_bf16; a.vbias = p->vbias; a.hbias = p->hbias; a.v = v; a.h = h; a.B = B;
+  a.W = p->W_bf16; a.W32 = p->W; a.vbias = p->vbias; a.hbias = p->hbias; a.v = v; a.h = h; a.B = B;
   a.nV = p->n_visible; a.nH = p->n_hidden; a.k = k; a.init_chains = init_chains;
   a.seed = seed; a.chain_offset = chain_offset; a.step_offset = step_offset;
   const bool fuse = S_vh != nullptr && smem_can_fuse_stats(p->n_visible, p->n_hidden);

@@ -17,6 +17,7 @@
 // The MMA of tile i+1 overlaps the epilogue of tile i through the two TMEM stages.
 // This file: the multi-step cluster kernel, the statistics GEMM, staging kernels and the host drivers
 // (umma_block_gibbs, umma_ais_run).
+#include <cmath>
 #include <vector>
 
 #include "umma_chain.cuh"
@@ -61,6 +62,14 @@ __global__ void pad_w_kernel(const uint16_t* __restrict__ W, uint16_t* __restric
   if (idx >= (int64_t)nVp * nHp) return;
   const int i = (int)(idx / nHp), j = (int)(idx % nHp);
   Wp[idx] = (i < nV && j < nH) ? W[(int64_t)i * nH + j] : (uint16_t)0;
+}
+// fp32 W -> padded bf16 (round to nearest even): the rounding lives in the library, so there is no bf16 copy of the
+// parameters outside the workspace that could go stale
+__global__ void pad_w_f32_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wp, int nV, int nH, int nVp, int nHp) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)nVp * nHp) return;
+  const int i = (int)(idx / nHp), j = (int)(idx % nHp);
+  Wp[idx] = __float2bfloat16_rn((i < nV && j < nH) ? W[(int64_t)i * nH + j] : 0.f);
 }
 // split weights: W = high + low with high = bf16(W), low = bf16(W - high); both zero padded
 __global__ void pad_w_split_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Whi, __nv_bfloat16* __restrict__ Wlo,
@@ -336,20 +345,25 @@ ChainCfg pick_chain_cfg(int nVp, int nHp, int64_t rows_pad, int sm_count) {
   if (force_bn == 64 || force_bn == 128 || force_bn == 256) {
     c.bn = force_bn;
   } else {
-    // fewest padded columns first; then the widest tile that still gives every SM >= 2 items per half-step
+    // fewest padded columns first; then the widest tile that still gives every SM an item per half-step
+    // (r02_chain_sweep1: at 1024^2 256-wide pair tiles win from 8192 chains up - 1022 vs 782 TFLOP/s for 128-wide)
     const int best = std::min(cols(64), std::min(cols(128), cols(256)));
     for (int bn : {256, 128, 64}) {
       if (cols(bn) != best) continue;
       c.bn = bn;
-      if (items(bn) >= 2 * (int64_t)sm_count) break;
+      if (items(bn) >= (int64_t)sm_count / 2) break;
     }
   }
   c.ctas = 1;
   if (c.bn == 256 && pairs_enabled()) {
-    const bool many = items(256) >= 8 * (int64_t)sm_count;
+    const bool many = items(256) >= (int64_t)sm_count;
     if (force_pairs == 1 || (force_pairs == -1 && many)) c.ctas = 2;
   }
   return c;
+}
+
+size_t chain_flag_bytes(int nVp, int nHp, int64_t rows_pad) {
+  return (size_t)2 * (size_t)(rows_pad / BLOCK_M) * (size_t)(round_up(std::max(nVp, nHp), 256) / 64) * 4;
 }
 
 struct Plan {
@@ -377,15 +391,25 @@ Plan make_plan(int nV, int nH, int64_t B) {
   p.wpart_ld = p.nHp / 32;
   p.off_wpart = o; o = align(o + (size_t)p.rows_pad * p.wpart_ld * 4);
   p.off_betas = o; o = align(o + (size_t)kMaxDeviceBetas * 4);   // AIS schedule for the chain kernel
-  p.off_flags = o; o = align(o + (size_t)(p.rows_pad / BLOCK_M) * 4);   // row-block arrival counters (chain kernel)
+  // chain kernel: arrival counters per (direction, 128-chain row block, 64-column chunk or wider)
+  p.off_flags = o; o = align(o + chain_flag_bytes(p.nVp, p.nHp, p.rows_pad));
   p.total = o + 1024;  // slack to align the caller's pointer
   return p;
 }
 
-// 1 (default): all half-steps in one dataflow launch (umma_chain.cuh); 0: one launch per half-step (round-1 path, A/B only)
-bool chain_enabled() {
-  static const bool on = env_int("RBM_B200_CHAIN", 1) != 0;
-  return on;
+// Dataflow chain kernel (umma_chain.cuh, all half-steps in ONE launch) or one launch per half-step?
+//   RBM_B200_CHAIN = 1: always the chain kernel; 0: always per-half-step launches; unset: by shape.
+// Measured at 1024 x 1024, sustained (profiles/r02_chain_vs_launches.txt): the chain kernel wins while a half-step
+// has few tiles per cluster - no partial last wave, no launch gap: 17.3 vs 23.0 us per half-step at 8,192 chains,
+// 65.3 vs 72.6 at 32,768 - and loses ~3 % at 65,536 chains (13.8 tiles per cluster; 130.6 vs 126.6 us), where the
+// launch tail is amortised and the per-tile dependency bookkeeping is not.
+bool chain_enabled(int nVp, int nHp, int64_t rows_pad, int sm_count) {
+  static const int mode = env_int("RBM_B200_CHAIN", -1);
+  if (mode >= 0) return mode != 0;
+  static const int max_items = env_int("RBM_B200_CHAIN_MAX_ITEMS", 10);
+  const ChainCfg cfg = pick_chain_cfg(nVp, nHp, rows_pad, sm_count);
+  const double items = (double)(rows_pad / (BLOCK_M * cfg.ctas)) * std::min(ceil_div(nVp, cfg.bn), ceil_div(nHp, cfg.bn));
+  return items < (double)max_items * std::max(1, sm_count / cfg.ctas);
 }
 
 // Launches the chain kernel over `steps` half-steps starting with direction 0.
@@ -413,12 +437,46 @@ int run_chain(const Plan& pl, uint16_t* Wp, uint16_t* Wlo, const float* nbh, con
   a.nbias[0] = nbh; a.nbias[1] = nbv; a.ldo[0] = pl.nHp; a.ldo[1] = pl.nVp;
   a.n_valid[0] = pl.nH; a.n_valid[1] = pl.nV;
   a.n_tiles[0] = ceil_div(pl.nHp, cfg.bn); a.n_tiles[1] = ceil_div(pl.nVp, cfg.bn);
-  a.split_k[0] = pl.nVp / BLOCK_K; a.split_k[1] = pl.nHp / BLOCK_K;
-  a.k_blocks[0] = a.split_k[0] * (split ? 2 : 1); a.k_blocks[1] = a.split_k[1] * (split ? 2 : 1);
+  a.k_blocks[0] = pl.nVp / BLOCK_K; a.k_blocks[1] = pl.nHp / BLOCK_K;
   a.m_groups = (int)(pl.rows_pad / (BLOCK_M * cfg.ctas));
   a.steps = steps; a.first_dir = 0; a.seed = seed; a.chain_offset = chain_offset; a.step_offset = step_offset;
   a.tag = tag; a.betas = betas_dev; a.wpart = wpart; a.wpart_ld = pl.wpart_ld; a.kf_magic = kKfMagic; a.flags = flags;
-  RBM_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)(pl.rows_pad / BLOCK_M) * 4, st));
+  a.row_blocks = (int)(pl.rows_pad / BLOCK_M);
+  // Publication policy (measured, profiles/r02_chain_opts.txt): a dependency warp polls ahead of the producer and the
+  // writer side needs no proxy fence in every case.  With fewer than ~2.5 items per cluster and half-step the call
+  // is bound by the half-step to half-step latency: chunks are published one by one, half a group after their
+  // store; with more items the consumers are far behind and a tile's chunks are published together.
+  static const int chain_opts_env = env_int("RBM_B200_CHAIN_OPTS", -1);
+  {
+    const double items_per_cluster = (double)a.m_groups * std::min(a.n_tiles[0], a.n_tiles[1]) / std::max(1, sm_count / cfg.ctas);
+    // (deferring a tile's last publication past the accumulator wait bought nothing: r02_chain_sweep5)
+    const int base = CHAIN_OPT_DEPWARP | CHAIN_OPT_CHUNKED | CHAIN_OPT_NO_WFENCE | CHAIN_OPT_NO_DEFER;
+    a.opts = chain_opts_env >= 0 ? chain_opts_env
+                                 : (items_per_cluster < 2.5 ? (base | CHAIN_OPT_MIDARRIVE) : (base | CHAIN_OPT_TILE_ARRIVE));
+  }
+  // chunks of 32 * kSets columns (EpiSplit): 128 for tiles >= 128 wide, 64 for 64-wide tiles
+  const int chunk_w = cfg.bn >= 128 ? 128 : 64;
+  a.chunks_ld = std::max(a.n_tiles[0], a.n_tiles[1]) * (cfg.bn / chunk_w);
+  RBM_REQUIRE((size_t)2 * a.row_blocks * a.chunks_ld * 4 <= chain_flag_bytes(pl.nVp, pl.nHp, pl.rows_pad),
+              RBM_B200_ERR_WORKSPACE, "chain kernel: counter region too small");
+  RBM_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)2 * a.row_blocks * a.chunks_ld * 4, st));
+  // Super-blocks: all half-steps for as many chains as keep both state tiles L2-resident, then the next chains.
+  // RBM_B200_CHAIN_SB = chains per super-block (0: automatic, -1: one super-block)
+  {
+    static const int sb_chains_env = env_int("RBM_B200_CHAIN_SB", 0);
+    DeviceInfo di;
+    if ((rc = get_device_info(&di))) return rc;
+    const int64_t group_rows = (int64_t)BLOCK_M * cfg.ctas;
+    const double bytes_per_chain = 2.0 * (pl.nVp + pl.nHp);
+    int64_t n_sb = 1;
+    if (sb_chains_env > 0) n_sb = ceil_div64(pl.rows_pad, sb_chains_env);
+    else if (sb_chains_env == 0) n_sb = (int64_t)std::ceil(pl.rows_pad * bytes_per_chain / (0.55 * (double)di.l2_bytes));
+    n_sb = std::max<int64_t>(1, std::min<int64_t>(n_sb, a.m_groups));
+    a.sb_groups = (int)ceil_div64(ceil_div64(pl.rows_pad, n_sb), group_rows);
+    // never so small that a half-step of a super-block has fewer than ~3 items per cluster (dependency slack)
+    const int min_groups = sb_chains_env > 0 ? 1 : ceil_div(3 * (sm_count / cfg.ctas), std::min(a.n_tiles[0], a.n_tiles[1]));
+    a.sb_groups = std::min(a.m_groups, std::max(a.sb_groups, min_groups));
+  }
   // every cluster must be resident (items wait for lower-numbered items of other clusters)
   static const int grid_cap = env_int("RBM_B200_CHAIN_GRID", 0);
   int64_t total_items = 0;
@@ -478,6 +536,16 @@ bool umma_variant_supported(int nV, int nH) { return nV >= 1 && nH >= 1 && nV <=
 
 size_t umma_workspace_bytes(int nV, int nH, int64_t B) { return make_plan(nV, nH, B).total; }
 
+// kernels one umma_block_gibbs call launches (no statistics): 3 parameter staging + 1 initial state + chain + 2 outputs
+int64_t umma_launch_count(int nV, int nH, int64_t B, int k, bool split_w) {
+  if (k <= 0) return 5;
+  const Plan pl = make_plan(nV, nH, B);
+  DeviceInfo di;
+  if (get_device_info(&di)) return -1;
+  const bool chain = split_w || chain_enabled(pl.nVp, pl.nHp, pl.rows_pad, di.sm_count);
+  return 6 + (chain ? 1 : 2 * (int64_t)k);
+}
+
 int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains,
                      uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws, size_t ws_bytes,
                      cudaStream_t st, float* S_vh, float* S_v, float* S_h, bool split_w) {
@@ -506,8 +574,11 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
     if (split_w)
       pad_w_split_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W, reinterpret_cast<__nv_bfloat16*>(Wp),
                                                                       reinterpret_cast<__nv_bfloat16*>(Wlo), pl.nV, pl.nH, pl.nVp, pl.nHp);
-    else
+    else if (p->W_bf16 != nullptr)
       pad_w_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W_bf16, Wp, pl.nV, pl.nH, pl.nVp, pl.nHp);
+    else
+      pad_w_f32_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W, reinterpret_cast<__nv_bfloat16*>(Wp), pl.nV, pl.nH,
+                                                                    pl.nVp, pl.nHp);
     const int nh256 = round_up(pl.nHp, 256), nv256 = round_up(pl.nVp, 256);
     nbias_kernel<<<ceil_div(nh256, 256), 256, 0, st>>>(p->hbias, nbh, pl.nH, nh256);
     nbias_kernel<<<ceil_div(nv256, 256), 256, 0, st>>>(p->vbias, nbv, pl.nV, nv256);
@@ -524,14 +595,13 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   int rc = check_launch("umma staging kernels");
   if (rc) return rc;
 
-  if (chain_enabled() && k > 0) {
+  if (k > 0 && (split_w || chain_enabled(pl.nVp, pl.nHp, pl.rows_pad, sm_count))) {
     // all 2k half-steps in ONE dataflow launch (umma_chain.cuh)
     uint32_t* flags = reinterpret_cast<uint32_t*>(base + pl.off_flags);
     if ((rc = run_chain<EPI_GIBBS, EPI_GIBBS>(pl, Wp, Wlo, nbh, nbv, Vs, Hs, flags, 2 * k, seed, chain_offset, step_offset,
                                               TAG_GIBBS, nullptr, nullptr, sm_count, st))) return rc;
   } else if (k > 0) {
     // round-1 path, kept for A/B measurements (RBM_B200_CHAIN=0): one launch per half-step
-    RBM_REQUIRE(Wlo == nullptr, RBM_B200_ERR_UNSUPPORTED, "split weights need the chain kernel (RBM_B200_CHAIN=0 is set)");
     static const int pairs_min_tiles = env_int("RBM_B200_PAIRS_MIN_TILES", 8);
     // tensor maps: states are K-major A operands; W is read MN-major (v->h) and K-major (h->v)
     CUtensorMap tm_w_mn, tm_w_k_single, tm_w_k_pair;
@@ -604,7 +674,7 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
   }
   const int sm_count = di.sm_count, cc_major = di.cc_major;
   RBM_REQUIRE(cc_major == 10, RBM_B200_ERR_NO_DEVICE, "AIS needs an sm_100 device (got cc %d.x)", cc_major);
-  const bool use_chain = chain_enabled() && n_betas <= kMaxDeviceBetas;
+  const bool use_chain = n_betas <= kMaxDeviceBetas && (split_w || chain_enabled(pl.nVp, pl.nHp, pl.rows_pad, sm_count));
   RBM_REQUIRE(!split_w || use_chain, RBM_B200_ERR_UNSUPPORTED,
               "AIS with split weights needs the chain kernel (at most %d betas)", kMaxDeviceBetas);
 
@@ -622,8 +692,11 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
     if (split_w)
       pad_w_split_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W, reinterpret_cast<__nv_bfloat16*>(Wp),
                                                                       reinterpret_cast<__nv_bfloat16*>(Wlo), pl.nV, pl.nH, pl.nVp, pl.nHp);
-    else
+    else if (p->W_bf16 != nullptr)
       pad_w_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W_bf16, Wp, pl.nV, pl.nH, pl.nVp, pl.nHp);
+    else
+      pad_w_f32_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p->W, reinterpret_cast<__nv_bfloat16*>(Wp), pl.nV, pl.nH,
+                                                                    pl.nVp, pl.nHp);
     const int nh256 = round_up(pl.nHp, 256), nv256 = round_up(pl.nVp, 256);
     nbias_kernel<<<ceil_div(nh256, 256), 256, 0, st>>>(p->hbias, nbh, pl.nH, nh256);
     nbias_kernel<<<ceil_div(nv256, 256), 256, 0, st>>>(p->vbias, nbv, pl.nV, nv256);

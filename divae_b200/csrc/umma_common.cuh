@@ -288,12 +288,25 @@ struct EpiSplit {
   static constexpr int kColsPerWarp = BLOCK_N / kSets;
 };
 
+// Per-group callbacks of epilogue_tile (the chain kernel publishes finished column chunks through them)
+struct NoGroupHooks {
+  __device__ __forceinline__ void mid(int) {}
+  __device__ __forceinline__ void before_store(int) {}
+  __device__ __forceinline__ void stored(int) {}
+};
+
 //   wrow       EPI_AIS_WEIGHT: this chain's log-weight slots, one per 32-unit group of hidden units (log2 units);
 //              the group's sum is ADDED with one red per thread, so the result does not depend on the tiling
-template <int BLOCK_N, int EPI, class WaitFn, class ReleaseFn>
+//   hooks      mid(g) is called half-way through group g, stored(g) after group g's box has been handed to TMA
+// Column mapping: the tile's 32-unit groups are dealt round-robin to the column sets, i.e. in round g the kSets
+// warps of a lane quarter cover the CONTIGUOUS chunk of columns [g * 32 kSets, (g + 1) * 32 kSets): the tile's
+// columns are finished chunk by chunk, not all at the very end.
+template <int BLOCK_N, int EPI, class WaitFn, class ReleaseFn, class Hooks>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtensorMap* tmap_out, uint32_t tmem_acc,
                                               int n_blk, int row_base, uint32_t chain, int quarter, int cq, int lane,
-                                              uint32_t stage_warp, float* wrow, WaitFn wait_full, ReleaseFn release) {
+                                              uint32_t stage_warp, float* wrow, WaitFn wait_full, ReleaseFn release,
+                                              Hooks& hooks) {
+  constexpr int kSets = EpiSplit<BLOCK_N>::kSets;
   constexpr int kColsPerWarp = EpiSplit<BLOCK_N>::kColsPerWarp;
   constexpr int kGroups = kColsPerWarp / 32;   // 32-unit Philox groups per warp per tile
   float wsum = 0.f;
@@ -305,7 +318,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
     // after the current group: the draw latency overlaps the wait / the TMA store.
     uint32_t w[4][4];
     auto draw_group = [&](int g) {
-      const uint32_t b0 = (uint32_t)((n_blk * BLOCK_N + cq * kColsPerWarp + g * 32) >> 5) * 4u;
+      const uint32_t b0 = (uint32_t)((n_blk * BLOCK_N + (g * kSets + cq) * 32) >> 5) * 4u;
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const uint4 x = draw_block(ep.ctx, b0 + b, chain);
@@ -318,7 +331,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
     tcgen05_fence_after();
 #pragma unroll 1
     for (int g = 0; g < kGroups; ++g) {
-      const int col_in_tile = cq * kColsPerWarp + g * 32;
+      const int col_in_tile = (g * kSets + cq) * 32;
       const int col0 = n_blk * BLOCK_N + col_in_tile;
       const bool live = col0 < ep.ldo;   // tile overhang beyond the padded unit count
       const uint32_t blk0 = (uint32_t)(col0 >> 5) * 4u;
@@ -329,6 +342,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
       }
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
+        if (hh == 1) hooks.mid(g);
         uint32_t r[16];
         tmem_ld16(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(col_in_tile + 16 * hh), r);
         tmem_ld_wait();
@@ -395,6 +409,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
       if (live && ep.debug_mode != 1) {
         // generic-proxy writes -> visible to the async proxy, then ONE coalesced TMA store of the
         // [32 chains x 32 units] box; columns beyond the padded unit count are clipped by TMA
+        hooks.before_store(g);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -406,6 +421,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
         atomicAdd(wrow + (col0 >> 5), wsum);   // one owner per (chain, group) and half-step: the order of adds is fixed
         wsum = 0.f;
       }
+      hooks.stored(g);
       if (g + 1 < kGroups) draw_group(g + 1);
     }
 }
@@ -699,13 +715,14 @@ umma_half_step_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (CTAS == 2) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(as), 0));   // the leader's barrier
         else mbar_arrive(tmem_empty_bar(as));
       };
+      NoGroupHooks no_hooks;
       if constexpr (EPI == EPI_LINEAR_SPLIT || EPI == EPI_LINEAR_F32)
         epilogue_tile_linear<BLOCK_N, EPI>(ep, &tmap_out, tmem_base + (uint32_t)(as * BLOCK_N), n_blk, row_base, quarter,
                                            cq, lane, stage_warp, wait_full, release);
       else
         epilogue_tile<BLOCK_N, EPI>(ep, &tmap_out, tmem_base + (uint32_t)(as * BLOCK_N), n_blk, row_base, chain, quarter,
                                     cq, lane, stage_warp, EPI == EPI_AIS_WEIGHT ? args.wpart + (size_t)row * args.wpart_ld : nullptr,
-                                    wait_full, release);
+                                    wait_full, release, no_hooks);
     }
     if (lane == 0) tma_store_wait_all();   // state tiles must be complete before the kernel ends
   }

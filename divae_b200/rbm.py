@@ -25,6 +25,7 @@ class RBM(nn.Module):
         self._visible_bias = nn.Parameter(torch.ones(n_visible) * 0.5, requires_grad=require_grad)
         self._hidden_bias = nn.Parameter(torch.zeros(n_hidden), requires_grad=require_grad)
         self._logZ = None          # set by estimate_logZ(); None -> the reference's placeholder
+        self._logZ_versions = None
         self._pack = _ops.ParamPack()
 
     # rbm.py:36-46
@@ -56,15 +57,27 @@ class RBM(nn.Module):
     def get_logZ_value(self):
         """rbm.py:51-54 returns the literal 33.65; an AIS estimate replaces it once computed."""
         if self._logZ is not None:
-            return self._logZ
+            if self._logZ_versions == self._param_versions():
+                return self._logZ
+            import warnings
+            warnings.warn("RBM parameters changed since estimate_logZ(): the stored log Z is stale, "
+                          "using the reference's literal 33.65 (call estimate_logZ() again)")
+            self._logZ = None
         return 33.65
 
-    def estimate_logZ(self, n_chains=16384, n_betas=10000, seed=0x5EED, betas=None, group=None, return_logw=False):
+    def _param_versions(self):
+        return tuple((p._version, p.data_ptr()) for p in (self._weights, self._visible_bias, self._hidden_bias))
+
+    def estimate_logZ(self, n_chains=16384, n_betas=10000, seed=0x5EED, betas=None, group=None, return_logw=False,
+                      variant="umma"):
         """Annealed-importance-sampling estimate of log Z (new capability; the reference hard-codes
         33.65, rbm.py:51-54).  Chains shard over the ranks of `group` (or the default process group
         when torch.distributed is initialised): every rank runs n_chains / world_size chains keyed by
         their global chain id and the log-weights are combined with an NCCL log-sum-exp.
-        Stores the estimate so that get_logZ_value() / log_prob() use it.  Algorithm: include/rbm_b200.h
+        `variant`: "umma" anneals with W rounded to bf16 (as the sampler draws); "umma_split" carries the fp32 W as
+        bf16 high + low parts (fp32-grade pre-activations, about twice the tensor time).
+        Stores the estimate, together with the parameter versions it was computed at, so that get_logZ_value() /
+        log_prob() use it until the parameters change (then they fall back to the reference's literal and warn).  Algorithm: include/rbm_b200.h
         (rbm_b200_ais_run), CPU restatement: oracle/rbm_oracle.py:ais_logZ."""
         import ctypes
         import math
@@ -81,19 +94,22 @@ class RBM(nn.Module):
         if betas is None:
             betas = np.linspace(0.0, 1.0, int(n_betas) + 1)
         betas = np.ascontiguousarray(betas, dtype=np.float64)
-        p, keep = self._pack.pack(self, need_bf16=True)
+        if variant not in ("umma", "umma_split", "auto"):
+            raise ValueError("estimate_logZ runs on the UMMA kernels: variant must be 'umma' or 'umma_split'")
+        p, keep = self._pack.pack(self)
         logw = torch.empty(n_local, dtype=torch.float64, device=dev)
         nbytes = lib.rbm_b200_ais_workspace(p.n_visible, p.n_hidden, n_local)
         ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=dev)
         with torch.no_grad(), torch.cuda.device(dev):
-            _lib.check(lib.rbm_b200_ais_run(ctypes.byref(p), n_local, betas.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                                            len(betas), int(seed) & 0xFFFFFFFFFFFFFFFF, offset, _ops._ptr(logw),
-                                            _ops._ptr(ws), nbytes, _ops._stream()), "ais_run")
+            _lib.check(lib.rbm_b200_ais_run_ex(ctypes.byref(p), n_local, betas.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                               len(betas), int(seed) & 0xFFFFFFFFFFFFFFFF, offset, _ops._ptr(logw),
+                                               _lib.VARIANTS[variant], _ops._ptr(ws), nbytes, _ops._stream()), "ais_run")
             lse = _dist.logsumexp_allreduce(logw, group=group)
             a = self._visible_bias.detach().double()
             logZA = p.n_hidden * math.log(2.0) + torch.nn.functional.softplus(a).sum()
             logZ = float((logZA + lse - math.log(n_chains)).item())
         self._logZ = logZ
+        self._logZ_versions = self._param_versions()
         if return_logw:
             return logZ, logw
         return logZ

@@ -24,7 +24,7 @@ from .baseSampler import BaseSampler
 
 class PCD(BaseSampler):
 
-    def __init__(self, batch_size, RBM, persistent=False, seed=None, variant="auto", chain_offset=0,
+    def __init__(self, batch_size, RBM, persistent=False, seed=None, variant="auto", chain_offset=None,
                  **kwargs):
         super(PCD, self).__init__(**kwargs)
         self._RBM = RBM
@@ -42,7 +42,11 @@ class PCD(BaseSampler):
         if variant not in _lib.VARIANTS:
             raise ValueError("variant must be one of %s" % sorted(_lib.VARIANTS))
         self._variant = _lib.VARIANTS[variant]
-        self._chain_offset = int(chain_offset)
+        # global id of this sampler's first chain.  None: 0 for a single process; under torch.distributed
+        # negative_phase() places the ranks' batches one after the other (rank r starts after the chains of ranks < r)
+        self._chain_offset_given = chain_offset is not None
+        self._chain_offset = int(chain_offset) if chain_offset is not None else 0
+        self._dist_layout = {}   # group id -> (first chain of this rank, total chains over the group)
         self._half_steps = 0  # draw counter: advances by 2k per call
         self._pack = _ops.ParamPack()
         self._workspace = None
@@ -78,8 +82,7 @@ class PCD(BaseSampler):
         if rbm is None or rbm is not self._modules.get("_RBM"):      # the submodule was replaced after construction
             rbm = self.__dict__["_rbm_plain"] = self._RBM
         B = self._batch_size
-        need_bf16 = self._variant not in (_lib.VARIANT_GENERAL, _lib.VARIANT_UMMA_SPLIT)
-        p, keep = self._pack.pack(rbm, need_bf16=need_bf16)     # raises for CPU parameters (no CPU fallback)
+        p, keep = self._pack.pack(rbm)     # raises for CPU parameters (no CPU fallback); fp32 only, W is rounded in-library
         dev = keep[0].device
         nV, nH = p.n_visible, p.n_hidden
         if v is None:
@@ -164,19 +167,40 @@ class PCD(BaseSampler):
         self._half_steps += 2 * k
         return v, h
 
+    def _group_layout(self, group):
+        """(first global chain id of this rank, total chains) for batches laid out rank after rank; one
+        all_gather of the batch sizes per (group, batch size), cached."""
+        key = (id(group), self._batch_size)
+        hit = self._dist_layout.get(key)
+        if hit is None:
+            dev = self._rbm_plain._weights.device if hasattr(self._rbm_plain, "_weights") else self._RBM.weights.device
+            world, rank = torch.distributed.get_world_size(group), torch.distributed.get_rank(group)
+            mine = torch.tensor([self._batch_size], dtype=torch.int64, device=dev)
+            sizes = [torch.zeros_like(mine) for _ in range(world)]
+            torch.distributed.all_gather(sizes, mine, group=group)
+            sizes = [int(x.item()) for x in sizes]
+            hit = self._dist_layout[key] = (sum(sizes[:rank]), sum(sizes))
+        return hit
+
     # ------------------------------------------------------------- negative phase (a15)
     def negative_phase(self, group=None):
         """Run the chain and return (energy_exp, (S_vh, S_v, S_h)).
 
         `energy_exp` equals GumBolt.energy_exp(v.detach(), h.detach()) (gumbolt.py:102-134) and
         backpropagates -<v h^T>, -<v>, -<h> into (W, a, c) without the [B,nV,nH] broadcast.
-        With a process group the statistics are sum-allreduced over chain shards (NCCL).
+        With a process group the statistics are sum-allreduced over chain shards (NCCL) and scaled by the TOTAL
+        chain count; unless `chain_offset` was given, rank r's chains follow those of ranks < r, so the result is
+        the statistic of one sum(B_r)-chain job (batch sizes may differ between ranks).
         """
-        world = 1
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(group)
-        v, h, (S, sv, sh), e = self.block_gibbs_sampling(_stats_scale=1.0 / (self._batch_size * world))
-        if world > 1:
+        distributed = group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())
+        total = self._batch_size
+        if distributed:
+            first, total = self._group_layout(group)
+            if not self._chain_offset_given:
+                # distinct chains on every rank: without this all ranks would draw chains [0, B) from the same seed
+                self._chain_offset = first
+        v, h, (S, sv, sh), e = self.block_gibbs_sampling(_stats_scale=1.0 / total)
+        if distributed and torch.distributed.get_world_size(group) > 1:
             from .. import dist as _dist
             S, sv, sh = _dist.allreduce_stats(S, sv, sh, group=group)
             e = None    # the local value covers this shard only: recompute from the allreduced statistics

@@ -71,8 +71,10 @@ enum {
 };
 
 /* RBM parameters (reference: RBM.__init__, models/rbm/rbm.py:28-34).
- * W is [n_visible, n_hidden] fp32; W_bf16 is the same matrix rounded to bf16
- * (round-to-nearest-even), required by the SMEM and UMMA variants, else NULL. */
+ * W is [n_visible, n_hidden] fp32.  W_bf16 is OPTIONAL: the same matrix rounded to bf16
+ * (round-to-nearest-even).  With W_bf16 == NULL the SMEM and UMMA variants round the fp32 W
+ * themselves while staging it (shared memory / workspace), so a caller that only keeps the
+ * fp32 parameters can never sample from a stale low-precision copy. */
 typedef struct {
   int32_t n_visible;
   int32_t n_hidden;
@@ -108,6 +110,11 @@ RBM_B200_API int rbm_b200_init_chains(float *v, int64_t B, int32_t n_visible, ui
 /* Bytes of caller-provided workspace rbm_b200_block_gibbs needs for this shape
  * and variant (0 for the GENERAL variant). Host only. */
 RBM_B200_API size_t rbm_b200_block_gibbs_workspace(int32_t n_visible, int32_t n_hidden, int64_t B, int variant);
+/* Number of CUDA kernels one rbm_b200_block_gibbs call with these arguments launches on the current
+ * device (the UMMA variant runs all 2k half-steps in ONE dataflow kernel when a half-step has few
+ * tiles per SM, else one kernel per half-step).  Host only; -1 without a device. */
+RBM_B200_API int64_t rbm_b200_block_gibbs_launch_count(int32_t n_visible, int32_t n_hidden, int64_t B,
+                                                       int32_t k, int variant);
 
 /* k steps of block Gibbs sampling: v <- v0; k x { h ~ p(h|v); v ~ p(v|h) }.
  * Replaces the loop of PCD.block_gibbs_sampling (pcd.py:51-69).  Returns the
@@ -213,6 +220,12 @@ RBM_B200_API size_t rbm_b200_ais_workspace(int32_t n_visible, int32_t n_hidden, 
 RBM_B200_API int rbm_b200_ais_run(const rbm_b200_params *p, int64_t n_chains, const double *betas,
                                   int32_t n_betas, uint64_t seed, uint64_t chain_offset, double *logw,
                                   void *workspace, size_t workspace_bytes, void *stream);
+/* Same, with the weight representation chosen explicitly: variant = RBM_B200_VARIANT_UMMA (or AUTO)
+ * rounds W to bf16 (from W_bf16 if given, else from the fp32 W inside the library);
+ * RBM_B200_VARIANT_UMMA_SPLIT carries the fp32 W as bf16 high + low parts. */
+RBM_B200_API int rbm_b200_ais_run_ex(const rbm_b200_params *p, int64_t n_chains, const double *betas,
+                                     int32_t n_betas, uint64_t seed, uint64_t chain_offset, double *logw,
+                                     int variant, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- next row: the decoder MLP applied to generated prior samples ------------
  * One fully connected layer y = x W^T + b in torch.nn.Linear layout

@@ -1,17 +1,29 @@
-"""Import shim for running the real reference in the BUILD CONTAINER only.
+"""Import shim for running the real, unmodified reference.
 
 TEST INFRASTRUCTURE.  Makes `from DiVAE import logging` (reference
-__init__.py:11-27) and `models.*` / `utils.*` importable from
-/root/reference, and stubs the third-party modules the reference imports but
+__init__.py:11-27) and `models.*` / `utils.*` / `engine.*` importable from
+the reference tree, and stubs the third-party modules the reference imports but
 this image lacks (hydra, torchviz, matplotlib, gif, h5py, coffea — none of them
-does arithmetic on the hot path).  Never used on the GPU box.
+does arithmetic on the hot path).  The tree is /root/reference in the build container and
+the staged copy baseline/_ref/DiVAE (baseline/stage_ref.py; git-ignored, shipped by gpurun)
+on the GPU box.
 """
 import importlib
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("DIVAE_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "DiVAE")
+
+
+def _find_root():
+    for cand in (os.environ.get("DIVAE_REFERENCE_ROOT"), "/root/reference", _STAGED):
+        if cand and os.path.isfile(os.path.join(cand, "models", "rbm", "rbm.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available():

@@ -21,7 +21,18 @@ CONFIGS = {
     "bn256": {"RBM_B200_CHAIN_BN": "256", "RBM_B200_CHAIN_PAIRS": "0"},
     "bn256_pairs": {"RBM_B200_CHAIN_BN": "256", "RBM_B200_CHAIN_PAIRS": "1"},
     "bn128_grid5": {"RBM_B200_CHAIN_BN": "128", "RBM_B200_CHAIN_GRID": "5"},   # few CTAs: a CTA waits on its own earlier items
+    "bn128_sb256": {"RBM_B200_CHAIN_BN": "128", "RBM_B200_CHAIN_SB": "256"},   # several super-blocks of 256 chains
+    "bn256_pairs_sb512": {"RBM_B200_CHAIN_BN": "256", "RBM_B200_CHAIN_PAIRS": "1", "RBM_B200_CHAIN_SB": "512"},
+    # publication policies (CHAIN_OPT_* bits, umma_chain.cuh): per-chunk at mid-group / per tile / producer-side polling
+    # without the dependency warp (a 256-wide tile over a 64-unit side once lost an arrival here) / never deferred
+    "bn256_opts15": {"RBM_B200_CHAIN_BN": "256", "RBM_B200_CHAIN_PAIRS": "0", "RBM_B200_CHAIN_OPTS": "15"},
+    "bn256_pairs_opts29": {"RBM_B200_CHAIN_BN": "256", "RBM_B200_CHAIN_PAIRS": "1", "RBM_B200_CHAIN_OPTS": "29"},
+    "bn256_opts4": {"RBM_B200_CHAIN_BN": "256", "RBM_B200_CHAIN_PAIRS": "0", "RBM_B200_CHAIN_OPTS": "4"},
+    "bn128_opts141": {"RBM_B200_CHAIN_BN": "128", "RBM_B200_CHAIN_OPTS": "141"},
+    "bn64_opts0": {"RBM_B200_CHAIN_BN": "64", "RBM_B200_CHAIN_OPTS": "0"},
 }
+ENV_KEYS = ("RBM_B200_CHAIN", "RBM_B200_CHAIN_BN", "RBM_B200_CHAIN_PAIRS", "RBM_B200_CHAIN_GRID", "RBM_B200_CHAIN_SB",
+            "RBM_B200_CHAIN_OPTS")
 
 
 @pytest.fixture(scope="module")
@@ -30,12 +41,12 @@ def results(tmp_path_factory):
     out = {}
     for name, extra in CONFIGS.items():
         env = dict(os.environ)
-        for key in ("RBM_B200_CHAIN", "RBM_B200_CHAIN_BN", "RBM_B200_CHAIN_PAIRS", "RBM_B200_CHAIN_GRID"):
+        for key in ENV_KEYS:
             env.pop(key, None)
         env.update(extra)
         path = str(d / (name + ".npz"))
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "chain_env_worker.py"), path], env=env,
-                           capture_output=True, text=True, timeout=600)
+                           capture_output=True, text=True, timeout=150)   # a dependency bug shows up as a hang
         assert r.returncode == 0, name + ": " + r.stderr[-3000:]
         out[name] = dict(np.load(path))
     return out

@@ -130,6 +130,11 @@ def _worker(rank, world, port, q):
         logw = torch.randn(40, dtype=torch.float64) * 5
         lse = bdist.logsumexp_allreduce(logw[off:off + n])
         ok = ok and abs(lse.item() - torch.logsumexp(logw, 0).item()) < 1e-9
+        # negative_phase() under a process group: the ranks' batches (sizes may differ) are laid out one after
+        # the other, so every rank draws its own chains and the statistics are scaled by the total count
+        s = divae_b200.PCD(5 + 2 * rank, divae_b200.RBM(6, 5), n_gibbs_sampling_steps=1, seed=3)
+        ok = ok and s._group_layout(None) == ((0, 12) if rank == 0 else (5, 12)) and not s._chain_offset_given
+        ok = ok and divae_b200.PCD(5, divae_b200.RBM(6, 5), n_gibbs_sampling_steps=1, seed=3, chain_offset=9)._chain_offset_given
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
