@@ -21,6 +21,14 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    msg = run_checks(rank, world, dev)
+    if rank == 0:
+        print(msg)
+    dist.destroy_process_group()
+
+
+def run_checks(rank, world, dev):
+    """All assertions of this file on an initialised process group (also run by bench.py before every N > 1 run)."""
     torch.manual_seed(32)
     total, k = 4096, 5
     for n, variant in ((256, "smem"), (512, "umma")):
@@ -34,12 +42,15 @@ def main():
         Sf, svf, shf = _ops.negative_phase_stats(vf, hf)
         off, nloc = bdist.shard_chains(total, rank, world)
         shard = divae_b200.PCD(batch_size=nloc, RBM=rbm, n_gibbs_sampling_steps=k, seed=77, variant=variant, chain_offset=off)
-        # negative_phase scales by 1/(B_local*world): make shards equal-sized for this check
-        assert total % world == 0
         e, (S, sv, sh) = shard.negative_phase()
         torch.testing.assert_close(S, Sf, rtol=0, atol=1e-6)
         torch.testing.assert_close(sv, svf, rtol=0, atol=1e-6)
         torch.testing.assert_close(sh, shf, rtol=0, atol=1e-6)
+        # default arguments (no chain_offset): the ranks' batches are laid out one after the other by negative_phase()
+        auto = divae_b200.PCD(batch_size=nloc, RBM=rbm, n_gibbs_sampling_steps=k, seed=77, variant=variant)
+        _, (S3, sv3, sh3) = auto.negative_phase()
+        torch.testing.assert_close(S3, Sf, rtol=0, atol=1e-6)
+        torch.testing.assert_close(sv3, svf, rtol=0, atol=1e-6)
         shard2 = divae_b200.PCD(batch_size=nloc, RBM=rbm, n_gibbs_sampling_steps=k, seed=77, variant=variant, chain_offset=off)
         vs, hs = shard2.block_gibbs_sampling()
         assert torch.equal(vs, vf[off:off + nloc]) and torch.equal(hs, hf[off:off + nloc])
@@ -98,9 +109,8 @@ def main():
     z_single = (64 * np.log(2.0) + torch.nn.functional.softplus(a).sum() + torch.logsumexp(logw, 0) - np.log(1024)).item()
     assert abs(z_sharded - z_single) < 1e-9, (z_sharded, z_single)
     dist.barrier()
-    if rank == 0:
-        print("multi-GPU checks ok on %d GPUs: shards == slices, allreduced stats == single-GPU stats, sharded generation == single-GPU generation, AIS log Z %.6f" % (world, z_sharded))
-    dist.destroy_process_group()
+    return ("multi-GPU checks ok on %d GPUs: shards == slices, allreduced stats == single-GPU stats, "
+            "sharded generation == single-GPU generation, AIS log Z %.6f" % (world, z_sharded))
 
 
 if __name__ == "__main__":

@@ -79,7 +79,7 @@ def test_edge_cases_k0_single_chain_and_missing_workspace(variant):
         assert rc == _lib.ERR_WORKSPACE and b"workspace" in lib.rbm_b200_last_error()
 
 
-def test_smem_variant_rejects_large_priors_and_missing_bf16():
+def test_smem_variant_rejects_large_priors_and_umma_needs_workspace():
     lib = _lib.load()
     W, a, c = rand_params(300, 64, 0.1, 4)
     rbm = make_rbm(W, a, c)
@@ -89,7 +89,8 @@ def test_smem_variant_rejects_large_priors_and_missing_bf16():
     assert rc == _lib.ERR_UNSUPPORTED
     p2, keep2 = rbm._pack.pack(rbm, need_bf16=False)
     rc = lib.rbm_b200_block_gibbs(ctypes.byref(p2), _ops._ptr(x), _ops._ptr(y), 4, 1, 1, 0, 0, 0, _lib.VARIANT_UMMA, None, 0, _ops._stream())
-    assert rc == _lib.ERR_INVALID and b"W_bf16" in lib.rbm_b200_last_error()
+    # W_bf16 is optional (the library rounds the fp32 W itself): what is missing here is the workspace
+    assert rc == _lib.ERR_WORKSPACE and b"workspace" in lib.rbm_b200_last_error()
 
 
 def test_bf16_weight_cache_follows_parameter_updates():

@@ -71,7 +71,9 @@ def test_bf16_rounded_chain_matches_fp32_chain_statistically(n, scale, B, varian
             # independent draws: |z| > 3 for 0.27 % of the entries; a rounding bias would push whole rows beyond it
             assert (z > 3).mean() < 0.01, (variant, name, float((z > 3).mean()))
             assert z.max() < 6.0, (variant, name, float(z.max()))
-            assert abs(np.sqrt((z ** 2).mean()) - np.sqrt((null ** 2).mean())) < 0.1, (variant, name, float(np.sqrt((z ** 2).mean())))
+            # one-sided: a bias inflates the z-scores; a smaller spread than the null's is sampling noise
+            # (256 marginals: the rms of |z| itself fluctuates by ~0.05)
+            assert np.sqrt((z ** 2).mean()) < np.sqrt((null ** 2).mean()) + 0.1, (variant, name, float(np.sqrt((z ** 2).mean())))
 
 
 @pytest.mark.parametrize("nV,nH,scale", [(256, 256, 0.3), (320, 192, 0.2), (1024, 1024, 0.1)])
