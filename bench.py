@@ -1,27 +1,37 @@
 #!/usr/bin/env python
-"""Benchmark of the RBM block-Gibbs hot path (BASELINE.json metric: unit-updates/s).
+"""Benchmark of the RBM block-Gibbs hot path (BASELINE.json metric: unit-updates/s at 1/2/4/8 B200).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU torch sampler
+  python bench.py --gpus N --steps K --warmup W                     # this repo's CUDA path, BASELINE configs[3]
+  python bench.py --gpus N --workload ais ...                       # BASELINE configs[4] (AIS log Z, NCCL log-sum-exp)
+  python bench.py --impl reference --gpus N --steps K --warmup W    # the reference's own CPU torch sampler
 
-Workload (config.workload): BASELINE.json configs[3] — "Large-prior shower generation:
-RBM 2x1024, 65,536 chains x 1000 Gibbs steps, chains sharded over 1/2/4/8 B200", the
-configuration the metric is quoted on at 1/2/4/8 GPUs.  One STEP = one
-PCD.block_gibbs_sampling() call = 65,536 chains x 1000 Gibbs steps on a 1024x1024 prior
-per GPU = 1.342e11 unit-updates (weak scaling: every rank runs 65,536 chains, chain ids
-offset by rank so the draws are those of one 65,536*N-chain job).  Synthetic data:
-reference-initialised parameters (models/rbm/rbm.py:28-34, torch.manual_seed(32)), chains
+Workload `gibbs` (default, config.workload): BASELINE.json configs[3] — "Large-prior shower generation: RBM
+2x1024, 65,536 chains x 1000 Gibbs steps, chains sharded over 1/2/4/8 B200".  One STEP = one
+PCD.block_gibbs_sampling() call on every rank = 65,536 chains x 1000 Gibbs steps on a 1024x1024 prior in total =
+1.342e11 unit-updates.  STRONG scaling by default: the 65,536 chains are split into contiguous blocks of global
+chain ids (divae_b200.dist.shard_chains; 8,192 per GPU at N=8) and, because every draw is keyed by the global chain
+id, the N-GPU job draws exactly what the 1-GPU job draws.  `--scaling weak` keeps 65,536 chains per GPU.
+Workload `ais`: BASELINE configs[4] — RBM 512x512, 16,384 annealing chains x 10,000 beta steps sharded over the
+ranks, one STEP = one RBM.estimate_logZ() call including the NCCL log-sum-exp of the log-weights.
+Synthetic data: reference-initialised parameters (models/rbm/rbm.py:28-34, torch.manual_seed(32)), chains
 initialised Bernoulli(1/2) on the device.
 
 Printed JSON (one line, rank 0):
-  value      device-resident throughput: inputs (W, a, c) already in HBM, CUDA events around
-             exactly K calls, max over ranks.
-  e2e        the same metric through the public API with HOST buffers: every step copies the
-             parameters host->device from pinned memory and the sampled (v, h) device->host.
-  roofline   tensor-pipe roofline of the dominant kernel (umma_half_step_kernel):
-             achieved = 2*B*nV*nH flops per launch / (timed call duration / 2k launches).
-  cpu_baseline  the reference sampler's torch port (oracle/ref_torch_port.py) on the host cores,
-             bounded sample of the same workload (rank 0, N=1 only).
+  value         device-resident throughput: inputs (W, a, c) already in HBM, CUDA events around exactly K calls,
+                max over ranks; whole-job aggregate (all ranks' unit-updates / that time).
+  e2e           the same metric through the public API with HOST buffers, over the same K steps: every step copies
+                the parameters host->device from pinned memory and the sampled (v, h) device->host.
+  roofline      tensor-pipe roofline of the dominant kernel: achieved = algorithmic flops of one rank's call
+                (2*B*nV*nH per half-step) / its measured duration, against MEASURED_PEAKS.json.
+  negphase      second timed leg (gibbs): PCD.negative_phase() = chain (k = 20) + statistics GEMM + ONE flat NCCL
+                sum-allreduce of [nV*nH + nV + nH] fp32 (collective C1) per call.
+  multi_gpu_check   N > 1: the assertions of tests/multi_gpu_check.py (shards == slices of the single-GPU job,
+                allreduced statistics == single-GPU statistics, sharded AIS == unsharded) run before the timing.
+  train         N = 1: BASELINE's second metric, DiVAE (GumBolt on EngineDiVAEpp.fit, the staged UNMODIFIED
+                reference model/engine) train samples/s with the reference's sampler on torch-CUDA vs the drop-in.
+  cpu_baseline  the reference's own PCD.block_gibbs_sampling (staged tree baseline/_ref, kind "reference"; the
+                op-for-op torch port oracle/ref_torch_port.py, kind "port", only when nothing is staged) on the
+                host cores, bounded sample of the same workload, threads swept over {1, n/2, n} (rank 0, N=1 only).
 """
 import argparse
 import json
@@ -36,10 +46,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_VISIBLE = N_HIDDEN = 1024
-CHAINS_PER_GPU = 65536
-GIBBS_STEPS = 1000
-WORKLOAD = "BASELINE configs[3]: RBM 1024x1024, 65536 chains/GPU x 1000 block-Gibbs steps per call"
+WORKLOADS = {
+    # name: (units per side, total chains, steps per call, description)
+    "gibbs": (1024, 65536, 1000, "BASELINE configs[3]: RBM 1024x1024, 65536 chains x 1000 block-Gibbs steps per call"),
+    "ais": (512, 16384, 10000, "BASELINE configs[4]: AIS log Z of RBM 512x512, 16384 annealing chains x 10000 beta steps per "
+                               "estimate, NCCL log-sum-exp of the log-weights"),
+}
+METRIC = "rbm_block_gibbs_unit_updates_per_s"
 
 
 def load_peaks():
@@ -112,128 +125,276 @@ def unit_updates(chains, k, nV, nH):
 
 
 # ------------------------------------------------------------------- CPU baseline / reference arm
-def time_cpu_port(nV, nH, chains, k, repeats, threads):
-    """Times oracle/ref_torch_port.block_gibbs_sampling (the reference's ATen op chain) on the host."""
-    import torch
-    from oracle import ref_torch_port as port
-    torch.set_num_threads(threads)
-    torch.manual_seed(32)
-    W = torch.randn(nV, nH) * 0.01
-    a = torch.ones(nV) * 0.5
-    c = torch.zeros(nH)
-    state = port.pcd_init_state(chains, nV)
-    best = None
-    with torch.no_grad():
-        port.block_gibbs_sampling(state[:64], W, a, c, 1)  # warm-up
-        for _ in range(repeats):
+def thread_sweep():
+    n = os.cpu_count() or 1
+    return sorted({1, max(1, n // 2), n})
+
+
+class CpuSampler:
+    """The reference's sampler on the host.  kind "reference": models.samplers.pcd.PCD / models.rbm.rbm.RBM imported
+    from the staged, unmodified tree (baseline/stage_ref.py -> baseline/_ref/DiVAE, through oracle/_ref_shim.py);
+    kind "port": oracle/ref_torch_port.py (the same ATen op chain) when no tree is staged."""
+
+    def __init__(self, n, chains, k):
+        import torch
+        self.n, self.chains, self.k = n, chains, k
+        torch.manual_seed(32)
+        self.kind = "port"
+        try:
+            from oracle import _ref_shim
+            if _ref_shim.reference_available():
+                _ref_shim.install()
+                for mod in [m for m in sys.modules if m.split(".")[0] == "models"]:
+                    del sys.modules[mod]      # never time a drop-in class registered under the reference's module path
+                from models.rbm.rbm import RBM
+                from models.samplers.pcd import PCD
+                self.rbm = RBM(n_visible=n, n_hidden=n)
+                self.sampler = PCD(batch_size=chains, RBM=self.rbm, n_gibbs_sampling_steps=k)
+                assert type(self.sampler).__module__ == "models.samplers.pcd" and "divae_b200" not in sys.modules.get(
+                    "models.samplers.pcd").__file__
+                self.kind = "reference"
+        except Exception as exc:    # a broken staging falls back to the port, loudly
+            print("bench.py: staged reference unusable (%r), timing the torch port instead" % (exc,), file=sys.stderr)
+            self.kind = "port"
+        if self.kind == "port":
+            from oracle import ref_torch_port as port
+            self.port = port
+            self.W = torch.randn(n, n) * 0.01
+            self.a = torch.ones(n) * 0.5
+            self.c = torch.zeros(n)
+            self.state = port.pcd_init_state(chains, n)
+
+    def describe(self):
+        return ("models/samplers/pcd.py PCD.block_gibbs_sampling of the staged reference tree" if self.kind == "reference"
+                else "oracle/ref_torch_port (the reference's ATen op chain, pcd.py:51-69)")
+
+    def call(self):
+        import torch
+        with torch.no_grad():
             t0 = time.perf_counter()
-            v, h, state = port.block_gibbs_sampling(state, W, a, c, k)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    return unit_updates(chains, k, nV, nH) / best, best
+            if self.kind == "reference":
+                self.sampler.block_gibbs_sampling()
+            else:
+                _, _, self.state = self.port.block_gibbs_sampling(self.state, self.W, self.a, self.c, self.k)
+            return time.perf_counter() - t0
+
+    def sweep(self, repeats=2):
+        """best seconds per call for every thread count of the sweep"""
+        import torch
+        out = {}
+        for t in thread_sweep():
+            torch.set_num_threads(t)
+            self.call()
+            out[t] = min(self.call() for _ in range(repeats))
+        return out
+
+
+def cpu_ais_port_call(n, chains, n_betas, state):
+    """AIS on the host in the reference's style (ATen op chain like pcd.py:23-49; the reference itself has NO estimator,
+    models/rbm/rbm.py:51-54 returns a literal): one matmul + softplus difference + draw per half-step."""
+    import torch
+    W, a, c, v = state
+    betas = torch.linspace(0.0, 1.0, n_betas + 1)
+    logw = torch.zeros(chains, dtype=torch.float64)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for k in range(1, n_betas + 1):
+            x = torch.matmul(v, W) + c
+            logw += (torch.nn.functional.softplus(betas[k] * x) - torch.nn.functional.softplus(betas[k - 1] * x)).sum(1).double()
+            h = (torch.sigmoid(betas[k] * x) >= torch.rand(x.size())).float()
+            v = (torch.sigmoid(a + betas[k] * torch.matmul(h, W.t())) >= torch.rand(v.size())).float()
+    state[3] = v
+    return time.perf_counter() - t0
 
 
 def cpu_baseline(args):
-    threads = os.cpu_count() or 1
-    chains, k = args.cpu_chains, args.cpu_steps
-    rate, dt = time_cpu_port(args.n, args.n, chains, k, repeats=2, threads=threads)
-    return {"value": rate, "unit": "unit-updates/s", "cores": threads, "kind": "port",
-            "sample": "oracle/ref_torch_port (reference ATen op chain, pcd.py:51-69) on RBM %dx%d, %d chains x %d steps, "
-                      "best of 2, %.2f s per call" % (args.n, args.n, chains, k, dt)}
+    n = args.n
+    if args.workload == "ais":
+        import torch
+        torch.manual_seed(32)
+        chains, nb = args.cpu_chains, args.cpu_steps
+        state = [torch.randn(n, n) * 0.01, torch.ones(n) * 0.5, torch.zeros(n), (torch.rand(chains, n) < 0.5).float()]
+        sweep = {}
+        for t in thread_sweep():
+            torch.set_num_threads(t)
+            cpu_ais_port_call(n, chains, 2, state)
+            sweep[t] = cpu_ais_port_call(n, chains, nb, state)
+        best_t = min(sweep, key=sweep.get)
+        return {"value": unit_updates(chains, nb, n, n) / sweep[best_t], "unit": "unit-updates/s", "cores": best_t,
+                "host_cpus": os.cpu_count(), "kind": "port",
+                "thread_sweep": {str(t): unit_updates(chains, nb, n, n) / s for t, s in sweep.items()},
+                "sample": "AIS in the reference's ATen style (the reference has no estimator) on RBM %dx%d, %d chains x %d betas"
+                          % (n, n, chains, nb)}
+    s = CpuSampler(n, args.cpu_chains, args.cpu_steps)
+    sweep = s.sweep()
+    best_t = min(sweep, key=sweep.get)
+    units = unit_updates(args.cpu_chains, args.cpu_steps, n, n)
+    return {"value": units / sweep[best_t], "unit": "unit-updates/s", "cores": best_t, "host_cpus": os.cpu_count(),
+            "kind": s.kind, "thread_sweep": {str(t): units / sec for t, sec in sweep.items()},
+            "sample": "%s on RBM %dx%d, %d chains x %d steps, torch.no_grad, best of 2 per thread count, %.2f s per call at "
+                      "%d threads" % (s.describe(), n, n, args.cpu_chains, args.cpu_steps, sweep[best_t], best_t)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    chains, k = args.cpu_chains, args.cpu_steps
     import torch
-    from oracle import ref_torch_port as port
+    n = args.n
+    chains, k = args.cpu_chains, args.cpu_steps
+    units = unit_updates(chains, k, n, n)
+    if args.workload == "ais":
+        torch.manual_seed(32)
+        state = [torch.randn(n, n) * 0.01, torch.ones(n) * 0.5, torch.zeros(n), (torch.rand(chains, n) < 0.5).float()]
+        kind, what = "port", "AIS in the reference's ATen style (the reference has no estimator)"
+        sweep = {}
+        for t in thread_sweep():
+            torch.set_num_threads(t)
+            sweep[t] = cpu_ais_port_call(n, chains, max(2, k // 4), state)
+        call = lambda: cpu_ais_port_call(n, chains, k, state)
+    else:
+        s = CpuSampler(n, chains, k)
+        kind, what = s.kind, s.describe()
+        sweep = s.sweep(repeats=1)
+        call = s.call
+    threads = min(sweep, key=sweep.get)
     torch.set_num_threads(threads)
-    torch.manual_seed(32)
-    W = torch.randn(args.n, args.n) * 0.01
-    a = torch.ones(args.n) * 0.5
-    c = torch.zeros(args.n)
-    state = port.pcd_init_state(chains, args.n)
     times = []
-    with torch.no_grad():
-        for i in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            v, h, state = port.block_gibbs_sampling(state, W, a, c, k)
-            dt = time.perf_counter() - t0
-            if i >= args.warmup:
-                times.append(dt)
+    for i in range(args.warmup + args.steps):
+        dt = call()
+        if i >= args.warmup:
+            times.append(dt)
     total = sum(times)
-    value = unit_updates(chains, k, args.n, args.n) * len(times) / total
-    sample = ("each step = reference sampler (torch port of models/samplers/pcd.py:51-69) on RBM %dx%d, %d chains x %d "
-              "Gibbs steps, %d host threads" % (args.n, args.n, chains, k, threads))
-    line = {"impl": "reference", "metric": "rbm_block_gibbs_unit_updates_per_s", "value": value, "unit": "unit-updates/s",
+    value = units * len(times) / total
+    sample = ("each step = %s on RBM %dx%d, %d chains x %d steps, %d host threads (best of the sweep %s of %d host CPUs)"
+              % (what, n, n, chains, k, threads, sorted(sweep), os.cpu_count() or 1))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "unit-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "unit-updates/s", "cores": threads, "kind": "port", "sample": sample},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload][3], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "unit-updates/s", "cores": threads, "host_cpus": os.cpu_count(),
+                             "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "unit-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------- GPU arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import divae_b200
-    from divae_b200 import _lib
+class Ctx:
+    """rank / device / timing helpers shared by the legs"""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load(build_if_missing=False)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    n, chains, k = args.n, args.chains, args.k
-    torch.manual_seed(32)                                   # scripts/run.py:17
-    rbm = divae_b200.RBM(n_visible=n, n_hidden=n).to(dev)   # reference init (rbm.py:28-34)
-    sampler = divae_b200.PCD(batch_size=chains, RBM=rbm, n_gibbs_sampling_steps=k, seed=0x5EED,
-                             variant=args.variant, chain_offset=rank * chains)
-    units_per_step = unit_updates(chains, k, n, n)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world > 1:
-            t = torch.tensor([x], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    def max_over_ranks(self, x):
+        if self.world > 1:
+            t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             return t.item()
         return x
 
+    def timed(self, fn, steps, warmup, clocks=False):
+        """ms per step: `warmup` untimed calls, then exactly `steps` calls between CUDA events on the current stream,
+        barrier + synchronize on both sides, MAX over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        cs = ClockSampler(self.local_rank) if (clocks and self.rank == 0) else None
+        if cs:
+            cs.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ck = cs.stop() if cs else {}
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps, ck
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def multi_gpu_precheck(ctx):
+    """tests/multi_gpu_check.py's assertions on this process group (a failure aborts the run on every rank)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import multi_gpu_check
+    t0 = time.perf_counter()
+    msg = multi_gpu_check.run_checks(ctx.rank, ctx.world, ctx.dev)
+    ctx.barrier()
+    return {"ok": True, "seconds": round(time.perf_counter() - t0, 2), "message": msg}
+
+
+def train_leg(dev, n_batches=40, batch=100):
+    """DiVAE train samples/s: the reference's GumBolt on EngineDiVAEpp.fit (engine/engineDiVAEpp.py:22-97, model
+    models/autoencoders/gumbolt.py:69-134; RBM 64x64 = BASELINE configs[1], PCD 100 chains x 10 steps) from the staged
+    tree, once with the reference's sampler (ATen on the same GPU) and once with the drop-in; same seeds and data."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_harness as rh
+    if not rh.reference_available():
+        return {"unavailable": "reference tree not staged (python baseline/stage_ref.py)"}
+    out = {"metric": "divae_train_samples_per_s", "unit": "samples/s", "model": "GumBolt 784 -> 2x64 latent, RBM 64x64, "
+           "PCD 100 chains x 10 steps, batch %d, %d iterations of EngineDiVAEpp.fit" % (batch, n_batches)}
+    for arm in ("reference", "dropin"):
+        ns = rh.load_arm(arm)
+        model, cfg = rh.build_gumbolt(ns, dev, n_latent_nodes=64, seed=0,
+                                      sampler_kwargs=dict(batch_size=100, n_gibbs_sampling_steps=10))
+        eng = rh.build_engine(ns, model, cfg, rh.SyntheticData(n_batches, batch, seed=7), dev)
+        eng.fit(1)                                 # warm-up epoch (allocator, autotuning, first-call staging)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loss = eng.fit(2)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[arm] = {"samples_per_s": n_batches * batch / dt, "ms_per_iteration": 1e3 * dt / n_batches,
+                    "final_loss": float(loss.detach()), "sampler": type(model.sampler).__module__}
+    out["speedup"] = out["dropin"]["samples_per_s"] / out["reference"]["samples_per_s"]
+    return out
+
+
+def run_gibbs(args, ctx):
+    import torch
+    import divae_b200
+    from divae_b200 import _lib, dist as bdist
+    lib = _lib.load(build_if_missing=False)
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    n, k = args.n, args.k
+    if args.scaling == "strong":
+        total = args.chains
+        offset, chains = bdist.shard_chains(total, rank, world)
+    else:
+        total, offset, chains = args.chains * world, rank * args.chains, args.chains
+    torch.manual_seed(32)                                   # scripts/run.py:17
+    rbm = divae_b200.RBM(n_visible=n, n_hidden=n).to(dev)   # reference init (rbm.py:28-34)
+    sampler = divae_b200.PCD(batch_size=chains, RBM=rbm, n_gibbs_sampling_steps=k, seed=0x5EED,
+                             variant=args.variant, chain_offset=offset)
+    units_per_step = unit_updates(total, k, n, n)
+
     # ---------------- device-resident: `value`
-    for _ in range(args.warmup):
-        sampler.block_gibbs_sampling()
-    barrier()
-    sampler_clock = ClockSampler(local_rank)
-    if rank == 0:
-        sampler_clock.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        v, h = sampler.block_gibbs_sampling()
-    e1.record()
-    barrier()
-    clocks = sampler_clock.stop() if rank == 0 else {}
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = ms_total / args.steps
-    value = world * units_per_step / (ms_per_step * 1e-3)
-    launches_per_step = 2 * k + 6   # 2k half-step GEMMs + W pad + 2 bias + init + 2 output conversions
+    ms_per_step, clocks = ctx.timed(sampler.block_gibbs_sampling, args.steps, args.warmup, clocks=True)
+    value = units_per_step / (ms_per_step * 1e-3)
+    variant_id = _lib.VARIANTS[args.variant]
+    launches_per_step = int(lib.rbm_b200_block_gibbs_launch_count(n, n, chains, k, variant_id))
 
     # ---------------- end to end through the public API with host buffers: `e2e`
     W_host = rbm.weights.detach().cpu().pin_memory()
@@ -251,47 +412,59 @@ def run_ours(args):
         v_host.copy_(vv, non_blocking=True)
         h_host.copy_(hh, non_blocking=True)
 
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    e2e_step()
-    barrier()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
+    e2e_steps = args.steps if args.e2e_steps <= 0 else max(1, min(args.steps, args.e2e_steps))
+    e2e_ms, _ = ctx.timed(e2e_step, e2e_steps, 1)
     h2d = 4 * (n * n + 2 * n)
     d2h = 4 * 2 * chains * n
     assert set(torch.unique(v_host[:256]).tolist()) <= {0.0, 1.0}
 
-    if rank != 0:
+    # ---------------- negative phase: chain + statistics GEMM + ONE flat NCCL allreduce (collective C1)
+    negphase = None
+    if not args.no_negphase:
+        np_sampler = divae_b200.PCD(batch_size=chains, RBM=rbm, n_gibbs_sampling_steps=args.negphase_k, seed=0xC1,
+                                    variant=args.variant, chain_offset=offset)
+        np_ms, _ = ctx.timed(lambda: np_sampler.negative_phase(), 20, 3)
+        ar_bytes = 4 * (n * n + 2 * n) if world > 1 else 0
+        ar_ms = None
         if world > 1:
-            dist.destroy_process_group()
-        return
+            S = torch.zeros(n, n, device=dev); sv = torch.zeros(n, device=dev); sh = torch.zeros(n, device=dev)
+            ar_ms, _ = ctx.timed(lambda: bdist.allreduce_stats(S, sv, sh), 50, 5)
+        negphase = {"ms": np_ms, "k": args.negphase_k, "chains": total, "chains_per_gpu": chains, "allreduce_bytes": ar_bytes,
+                    "allreduce_ms": ar_ms, "unit_updates_per_s": unit_updates(total, args.negphase_k, n, n) / (np_ms * 1e-3),
+                    "what": "PCD.negative_phase(): k-step chain + <vh>,<v>,<h> statistics GEMM + one flat NCCL sum-allreduce"}
 
+    if rank != 0:
+        return None
     peaks = load_peaks()
-    flops_per_launch = 2.0 * chains * n * n
-    launch_ms = ms_per_step / (2 * k)
-    achieved = flops_per_launch / (launch_ms * 1e-3) / 1e12
+    chain_kernel = launches_per_step < 2 * k
+    flops_per_call = 4.0 * chains * k * n * n
+    achieved = flops_per_call / (ms_per_step * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get("umma_half_step_dram_bytes_per_launch")
+                tj = json.load(f)
+            traffic = tj.get("umma_chain_dram_bytes_per_half_step_8192" if chain_kernel else "umma_half_step_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    default = (n, args.chains, k) == WORKLOADS["gibbs"][:3]
     line = {
-        "metric": "rbm_block_gibbs_unit_updates_per_s", "value": value, "unit": "unit-updates/s",
+        "metric": METRIC, "value": value, "unit": "unit-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD if (n, chains, k) == (N_VISIBLE, CHAINS_PER_GPU, GIBBS_STEPS)
-                   else "RBM %dx%d, %d chains/GPU x %d steps (non-default)" % (n, n, chains, k),
-                   "n_visible": n, "n_hidden": n, "chains_per_gpu": chains, "gibbs_steps": k,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOADS["gibbs"][3] if default else "RBM %dx%d, %d chains x %d steps (non-default)" % (n, n, total, k),
+                   "n_visible": n, "n_hidden": n, "chains_total": total, "chains_per_gpu": chains, "gibbs_steps": k,
                    "variant": args.variant, "seed": "0x5EED",
-                   "l2": "state tiles (2 x %d MiB bf16) + fp32 outputs exceed the 126 MB L2; no explicit flush"
-                         % (chains * n * 2 >> 20)},
-        "e2e": {"value": world * units_per_step / (e2e_ms * 1e-3), "unit": "unit-updates/s",
+                   "kernel_path": "umma_chain_kernel (all 2k half-steps in one dataflow launch)" if chain_kernel
+                                  else "umma_half_step_kernel (one launch per half-step)",
+                   "l2": "between timed calls the fp32 outputs (2 x %d MiB written per call) and the re-initialised state tiles "
+                         "(2 x %d MiB bf16) are rewritten%s; no explicit flush"
+                         % (chains * n * 4 >> 20, chains * n * 2 >> 20,
+                            " and exceed the 126 MB L2" if chains * n * 12 > 126e6 else
+                            " (working set below the 126 MB L2: the chain kernel keeps states L2-resident by design, "
+                            "W is 2 MiB)")},
+        "e2e": {"value": units_per_step / (e2e_ms * 1e-3), "unit": "unit-updates/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
@@ -299,15 +472,104 @@ def run_ours(args):
                    "power_w": clocks.get("power_w")},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
-                     "kernel": "umma_half_step_kernel", "flops_per_launch": flops_per_launch,
-                     "launch_ms": launch_ms, "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                     "kernel": "umma_chain_kernel" if chain_kernel else "umma_half_step_kernel",
+                     "flops_per_launch": flops_per_call if chain_kernel else flops_per_call / (2 * k),
+                     "launch_ms": ms_per_step if chain_kernel else ms_per_step / (2 * k),
+                     "half_step_us": 1e3 * ms_per_step / (2 * k),
+                     "peak_source": peaks["source"] + " bf16_tflops_sustained (per GPU; achieved is rank 0's share of the job)",
                      "frac_of_burst": achieved / peaks["tflops_burst"]},
     }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if negphase is not None:
+        line["negphase"] = negphase
+    return line
+
+
+def run_ais(args, ctx):
+    import numpy as np
+    import torch
+    import divae_b200
+    from divae_b200 import _lib, dist as bdist
+    _lib.load(build_if_missing=False)
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    n, K = args.n, args.k
+    if args.scaling == "strong":
+        total = args.chains
+    else:
+        total = args.chains * world
+    _, chains = bdist.shard_chains(total, rank, world)
+    torch.manual_seed(32)
+    rbm = divae_b200.RBM(n_visible=n, n_hidden=n).to(dev)
+    with torch.no_grad():
+        rbm._weights.mul_(5.0)          # sigma 0.05: a prior whose log Z is not the trivial one of W ~ 0
+    betas = np.linspace(0.0, 1.0, K + 1)
+    results = []
+
+    def step():
+        results.append(rbm.estimate_logZ(n_chains=total, betas=betas, seed=0x5EED, variant=args.ais_variant))
+
+    units_per_step = unit_updates(total, K, n, n)
+    ms_per_step, clocks = ctx.timed(step, args.steps, args.warmup, clocks=True)
+    value = units_per_step / (ms_per_step * 1e-3)
+
+    W_host = rbm.weights.detach().cpu().pin_memory()
+    a_host = rbm.visible_bias.detach().cpu().pin_memory()
+    c_host = rbm.hidden_bias.detach().cpu().pin_memory()
+
+    def e2e_step():
+        with torch.no_grad():
+            rbm._weights.copy_(W_host, non_blocking=True)
+            rbm._visible_bias.copy_(a_host, non_blocking=True)
+            rbm._hidden_bias.copy_(c_host, non_blocking=True)
+        step()      # betas travel host -> device inside the call, the estimate comes back with .item()
+
+    e2e_ms, _ = ctx.timed(e2e_step, args.steps, 1)
+    if rank != 0:
+        return None
+    peaks = load_peaks()
+    flops_per_call = (2 * K - 1) * 2.0 * chains * n * n
+    achieved = flops_per_call / (ms_per_step * 1e-3) / 1e12
+    default = (n, args.chains, K) == WORKLOADS["ais"][:3]
+    return {
+        "metric": METRIC, "value": value, "unit": "unit-updates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOADS["ais"][3] if default else "AIS RBM %dx%d, %d chains x %d betas (non-default)" % (n, n, total, K),
+                   "n_visible": n, "n_hidden": n, "chains_total": total, "chains_per_gpu": chains, "beta_steps": K,
+                   "variant": args.ais_variant, "seed": "0x5EED", "weights": "randn * 0.05",
+                   "collective": "NCCL allreduce(max) + allreduce(sum) of the log-weights inside every timed step" if world > 1 else "none (1 GPU)",
+                   "log_Z": results[-1], "log_Z_spread": max(results) - min(results),
+                   "l2": "state tiles are L2-resident by design (2 x %d KiB bf16 per GPU); W 512 KiB" % (chains * n * 2 >> 10)},
+        "e2e": {"value": units_per_step / (e2e_ms * 1e-3), "unit": "unit-updates/s", "h2d_bytes_per_step": 4 * (n * n + 2 * n) + 4 * (K + 1),
+                "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms, "steps": args.steps},
+        "gpu_launches": 8 * args.steps,     # 3 parameter staging + memset-free init + chain + reduce (+ torch's reductions)
+        "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
+                   "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0), "power_w": clocks.get("power_w")},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tflops_sustained"], "traffic": None, "kernel": "umma_chain_kernel (AIS flavour)",
+                     "flops_per_launch": flops_per_call, "launch_ms": ms_per_step, "half_step_us": 1e3 * ms_per_step / (2 * K - 1),
+                     "peak_source": peaks["source"] + " bf16_tflops_sustained (per GPU)",
+                     "frac_of_burst": achieved / peaks["tflops_burst"]},
+    }
+
+
+def run_ours(args):
+    ctx = Ctx()
+    precheck = None
+    if ctx.world > 1 and not args.no_precheck:
+        precheck = multi_gpu_precheck(ctx)
+    line = run_ais(args, ctx) if args.workload == "ais" else run_gibbs(args, ctx)
+    if ctx.rank == 0:
+        if precheck is not None:
+            line["multi_gpu_check"] = precheck
+        if ctx.world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        if ctx.world == 1 and not args.no_train and args.workload == "gibbs":
+            try:
+                line["train"] = train_leg(ctx.dev)
+            except Exception as exc:   # the secondary metric must never take the headline line down
+                line["train"] = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+        print(json.dumps(line), flush=True)
+    ctx.finish()
 
 
 def main():
@@ -316,15 +578,31 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_VISIBLE, help="units per RBM side")
-    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
-    ap.add_argument("--k", type=int, default=GIBBS_STEPS, help="Gibbs steps per call")
+    ap.add_argument("--workload", default="gibbs", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --chains is the whole job, sharded over the ranks; weak: --chains per GPU")
+    ap.add_argument("--n", type=int, default=None, help="units per RBM side")
+    ap.add_argument("--chains", type=int, default=None, help="chains of the whole job (strong) / per GPU (weak)")
+    ap.add_argument("--k", type=int, default=None, help="Gibbs steps per call / AIS beta steps")
     ap.add_argument("--variant", default="auto")
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-chains", type=int, default=4096, help="bounded CPU sample: chains")
-    ap.add_argument("--cpu-steps", type=int, default=10, help="bounded CPU sample: Gibbs steps")
+    ap.add_argument("--ais-variant", default="umma", choices=["umma", "umma_split"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0: as many as --steps")
+    ap.add_argument("--negphase-k", type=int, default=20)
+    ap.add_argument("--cpu-chains", type=int, default=None, help="bounded CPU sample: chains")
+    ap.add_argument("--cpu-steps", type=int, default=None, help="bounded CPU sample: Gibbs / beta steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-negphase", action="store_true")
+    ap.add_argument("--no-precheck", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
+    n, chains, k, _ = WORKLOADS[args.workload]
+    args.n = n if args.n is None else args.n
+    args.chains = chains if args.chains is None else args.chains
+    args.k = k if args.k is None else args.k
+    if args.cpu_chains is None:
+        args.cpu_chains = 4096 if args.workload == "gibbs" else 2048
+    if args.cpu_steps is None:
+        args.cpu_steps = 10 if args.workload == "gibbs" else 40
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -38,6 +38,32 @@ print(json.dumps({"n": n, "chains": B, "k": k, "variant": "%(variant)s", "ms_per
                   "mean_v": float(v.mean())}))
 """
 
+AIS_WORKER = r"""
+import json, os, sys, torch, numpy as np
+sys.path.insert(0, %(root)r)
+import divae_b200
+n, M, K, reps = %(n)d, %(B)d, %(k)d, %(reps)d
+torch.manual_seed(32)
+rbm = divae_b200.RBM(n, n)
+with torch.no_grad():
+    rbm._weights.mul_(5.0)
+rbm = rbm.to("cuda:0")
+betas = np.linspace(0.0, 1.0, K + 1)
+z = rbm.estimate_logZ(n_chains=M, betas=betas, seed=0x5EED, variant="%(variant)s")
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    z = rbm.estimate_logZ(n_chains=M, betas=betas, seed=0x5EED, variant="%(variant)s")
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+us = ms * 1e3 / (2 * K - 1)
+print(json.dumps({"ais": True, "n": n, "chains": M, "betas": K, "variant": "%(variant)s", "ms_per_call": ms, "us_per_half_step": us,
+                  "tflops": 2.0 * M * n * n / (us * 1e-6) / 1e12, "unit_updates_per_s": M * K * 2 * n / (ms * 1e-3),
+                  "log_Z": z}))
+"""
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -48,6 +74,7 @@ def main():
     ap.add_argument("--variant", default="umma")
     ap.add_argument("--configs", default="launches,bn256p,bn256,bn128,bn64,auto")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--ais", action="store_true", help="time RBM.estimate_logZ (k = beta steps) instead of block Gibbs sampling")
     args = ap.parse_args()
     envs = {
         "launches": {"RBM_B200_CHAIN": "0"},
@@ -78,7 +105,7 @@ def main():
             if name.startswith("opts") and name not in envs:
                 envs[name] = {"RBM_B200_CHAIN_OPTS": name[4:]}
             env.update(envs[name])
-            code = WORKER % dict(root=ROOT, n=args.n, B=B, k=args.k, reps=args.reps, variant=args.variant)
+            code = (AIS_WORKER if args.ais else WORKER) % dict(root=ROOT, n=args.n, B=B, k=args.k, reps=args.reps, variant=args.variant)
             try:
                 r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
             except subprocess.TimeoutExpired:

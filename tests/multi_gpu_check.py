@@ -103,8 +103,10 @@ def run_checks(rank, world, dev):
     logw = torch.empty(1024, dtype=torch.float64, device=dev)
     nbytes = lib.rbm_b200_ais_workspace(96, 64, 1024)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    _lib.check(lib.rbm_b200_ais_run(ctypes.byref(p), 1024, betas.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 101, 5, 0,
-                                    _ops._ptr(logw), _ops._ptr(ws), nbytes, _ops._stream()))
+    # same weight representation as estimate_logZ's default (W rounded to bf16 in the library); the legacy entry
+    # rbm_b200_ais_run without a W_bf16 pointer would anneal with split (fp32-grade) weights: 0.02 nats away here
+    _lib.check(lib.rbm_b200_ais_run_ex(ctypes.byref(p), 1024, betas.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 101, 5, 0,
+                                       _ops._ptr(logw), _lib.VARIANTS["umma"], _ops._ptr(ws), nbytes, _ops._stream()))
     a = rbm._visible_bias.detach().double()
     z_single = (64 * np.log(2.0) + torch.nn.functional.softplus(a).sum() + torch.logsumexp(logw, 0) - np.log(1024)).item()
     assert abs(z_sharded - z_single) < 1e-9, (z_sharded, z_single)

@@ -18,7 +18,9 @@ def test_reference_arm_prints_one_json_line_with_required_keys():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "unit-updates/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the staged / mounted reference tree when there is one, else the op-for-op port
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["scaling"] == "strong"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["vs_baseline"] is None and "workload" in d["config"]
 
@@ -35,3 +37,24 @@ def test_graft_entry_build_produces_the_library():
     import __graft_entry__ as ge
     lib = ge.build()
     assert os.path.isfile(lib) and lib.endswith("librbm_b200.so")
+
+
+def test_reference_arm_times_the_reference_classes_when_the_tree_is_present():
+    sys.path.insert(0, ROOT)
+    from oracle import _ref_shim
+    if not _ref_shim.reference_available():
+        import pytest
+        pytest.skip("no reference tree")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-chains", "32", "--cpu-steps", "1", "--n", "64"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["kind"] == "reference" and "models/samplers/pcd.py" in d["config"]["sample"]
+
+
+def test_ais_reference_arm_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "ais", "--steps", "1",
+                          "--warmup", "0", "--cpu-chains", "16", "--cpu-steps", "8", "--n", "64"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and "configs[4]" in d["config"]["workload"]
