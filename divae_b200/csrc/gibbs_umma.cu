@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "umma_chain.cuh"
+#include "umma_resident.cuh"
 
 namespace rbm {
 namespace {
@@ -488,6 +489,43 @@ int run_chain(const Plan& pl, uint16_t* Wp, uint16_t* Wlo, const float* nbh, con
   return launch_chain<EPI0, EPI1>(cfg.bn, cfg.ctas, split, tm, a, grid, st);
 }
 
+// Resident kernel (umma_resident.cuh): W in shared memory, states exchanged as bit words inside a cluster.
+//   RBM_B200_RESIDENT = 1: whenever the shape fits; 0: never; unset: by shape.
+// Measured on B200 (profiles/r02_resident_vs_chain.txt, us per half-step): 512 x 512 Gibbs 3.96 vs 7.13 at 1,024 chains
+// and 5.55 vs 7.91 at 3,840; AIS 4.76 vs 8.2 and 6.7 vs 9.3; 256 x 256 2.87 vs 5.97.  Its time grows in steps of one
+// "round" (two row blocks on every resident cluster: 30 x 128 chains), so beyond one round the dataflow chain kernel,
+// which fills all SMs, takes over.
+bool resident_enabled(int nVp, int nHp, int64_t rows_pad, bool split_w, int sm_count) {
+  static const int mode = env_int("RBM_B200_RESIDENT", -1);
+  if (split_w || !resident_supported(nVp, nHp)) return false;
+  if (mode >= 0) return mode != 0;
+  const int cluster = resident_cluster_size(nHp / kResBN, nVp / kResBN);
+  int max_clusters = 0;
+  if (resident_max_clusters<EPI_GIBBS, EPI_GIBBS>(cluster, resident_smem(nHp / kResBN, nVp / kResBN).total, sm_count, &max_clusters))
+    return false;
+  return rows_pad / BLOCK_M <= 2 * (int64_t)max_clusters;
+}
+
+template <int EPI0, int EPI1>
+int run_resident(const Plan& pl, uint16_t* Wp, const float* nbh, const float* nbv, __nv_bfloat16* Vs, __nv_bfloat16* Hs,
+                 int steps, uint64_t seed, uint64_t chain_offset, uint64_t step_offset, uint32_t tag,
+                 const float* betas_dev, float* wpart, int sm_count, cudaStream_t st) {
+  int rc;
+  CUtensorMap tm_w;
+  // one [64 x 64] box serves both directions: (v rows = k, h cols = n) MN-major, (v rows = n, h cols = k) K-major
+  if ((rc = make_tmap(&tm_w, Wp, (uint64_t)pl.nVp, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
+  ResidentArgs a{};
+  a.nbias[0] = nbh; a.nbias[1] = nbv;
+  a.n_valid[0] = pl.nH; a.n_valid[1] = pl.nV;
+  a.n_tiles[0] = pl.nHp / kResBN; a.n_tiles[1] = pl.nVp / kResBN;
+  a.ld[0] = pl.nHp; a.ld[1] = pl.nVp;
+  a.row_blocks = (int)(pl.rows_pad / BLOCK_M);
+  a.steps = steps; a.seed = seed; a.chain_offset = chain_offset; a.step_offset = step_offset; a.tag = tag;
+  a.betas = betas_dev; a.wpart = wpart; a.wpart_ld = pl.wpart_ld; a.kf_magic = kKfMagic;
+  a.v_init = Vs; a.out[0] = Hs; a.out[1] = Vs;
+  return launch_resident<EPI0, EPI1>(tm_w, a, resident_cluster_size(a.n_tiles[0], a.n_tiles[1]), sm_count, st);
+}
+
 template <int BLOCK_N>
 int launch_stats(const CUtensorMap& tv, const CUtensorMap& th, const StatsArgs& a, int grid, cudaStream_t st) {
   auto kern = umma_stats_kernel<BLOCK_N>;
@@ -532,6 +570,14 @@ int umma_stats(const Plan& pl, const __nv_bfloat16* Vs, const __nv_bfloat16* Hs,
 
 }  // namespace
 
+#ifdef RBM_RES_TRACE
+}  // namespace rbm
+extern "C" __attribute__((visibility("default"))) int rbm_b200_debug_resident_trace(unsigned long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, rbm::g_res_trace, sizeof(unsigned long long) * (size_t)n);
+}
+namespace rbm {
+#endif
+
 bool umma_variant_supported(int nV, int nH) { return nV >= 1 && nH >= 1 && nV <= 16384 && nH <= 16384; }
 
 size_t umma_workspace_bytes(int nV, int nH, int64_t B) { return make_plan(nV, nH, B).total; }
@@ -542,7 +588,8 @@ int64_t umma_launch_count(int nV, int nH, int64_t B, int k, bool split_w) {
   const Plan pl = make_plan(nV, nH, B);
   DeviceInfo di;
   if (get_device_info(&di)) return -1;
-  const bool chain = split_w || chain_enabled(pl.nVp, pl.nHp, pl.rows_pad, di.sm_count);
+  const bool chain = split_w || resident_enabled(pl.nVp, pl.nHp, pl.rows_pad, split_w, di.sm_count) ||
+                     chain_enabled(pl.nVp, pl.nHp, pl.rows_pad, di.sm_count);
   return 6 + (chain ? 1 : 2 * (int64_t)k);
 }
 
@@ -595,7 +642,11 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   int rc = check_launch("umma staging kernels");
   if (rc) return rc;
 
-  if (k > 0 && (split_w || chain_enabled(pl.nVp, pl.nHp, pl.rows_pad, sm_count))) {
+  if (k > 0 && resident_enabled(pl.nVp, pl.nHp, pl.rows_pad, split_w, sm_count)) {
+    // priors up to 512 x 512: W resident in shared memory, states on the chip (umma_resident.cuh)
+    if ((rc = run_resident<EPI_GIBBS, EPI_GIBBS>(pl, Wp, nbh, nbv, Vs, Hs, 2 * k, seed, chain_offset, step_offset, TAG_GIBBS,
+                                                 nullptr, nullptr, sm_count, st))) return rc;
+  } else if (k > 0 && (split_w || chain_enabled(pl.nVp, pl.nHp, pl.rows_pad, sm_count))) {
     // all 2k half-steps in ONE dataflow launch (umma_chain.cuh)
     uint32_t* flags = reinterpret_cast<uint32_t*>(base + pl.off_flags);
     if ((rc = run_chain<EPI_GIBBS, EPI_GIBBS>(pl, Wp, Wlo, nbh, nbv, Vs, Hs, flags, 2 * k, seed, chain_offset, step_offset,
@@ -674,7 +725,9 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
   }
   const int sm_count = di.sm_count, cc_major = di.cc_major;
   RBM_REQUIRE(cc_major == 10, RBM_B200_ERR_NO_DEVICE, "AIS needs an sm_100 device (got cc %d.x)", cc_major);
-  const bool use_chain = n_betas <= kMaxDeviceBetas && (split_w || chain_enabled(pl.nVp, pl.nHp, pl.rows_pad, sm_count));
+  const bool use_resident = n_betas <= kMaxDeviceBetas && resident_enabled(pl.nVp, pl.nHp, pl.rows_pad, split_w, sm_count);
+  const bool use_chain = use_resident ||
+                         (n_betas <= kMaxDeviceBetas && (split_w || chain_enabled(pl.nVp, pl.nHp, pl.rows_pad, sm_count)));
   RBM_REQUIRE(!split_w || use_chain, RBM_B200_ERR_UNSUPPORTED,
               "AIS with split weights needs the chain kernel (at most %d betas)", kMaxDeviceBetas);
 
@@ -718,8 +771,11 @@ int umma_ais_run(const rbm_b200_params* p, int64_t M, const double* betas, int n
     // pageable source: the runtime stages the copy before returning, so `bf` may go out of scope
     RBM_CUDA_TRY(cudaMemcpyAsync(betas_dev, bf.data(), sizeof(float) * (size_t)n_betas, cudaMemcpyHostToDevice, st));
     uint32_t* flags = reinterpret_cast<uint32_t*>(base + pl.off_flags);
-    if ((rc = run_chain<EPI_AIS_WEIGHT, EPI_ANNEALED>(pl, Wp, Wlo, nbh, nbv, Vs, Hs, flags, 2 * K - 1, seed, chain_offset, 2,
-                                                      TAG_AIS, betas_dev, wpart, sm_count, st))) return rc;
+    if (use_resident) {
+      if ((rc = run_resident<EPI_AIS_WEIGHT, EPI_ANNEALED>(pl, Wp, nbh, nbv, Vs, Hs, 2 * K - 1, seed, chain_offset, 2, TAG_AIS,
+                                                           betas_dev, wpart, sm_count, st))) return rc;
+    } else if ((rc = run_chain<EPI_AIS_WEIGHT, EPI_ANNEALED>(pl, Wp, Wlo, nbh, nbv, Vs, Hs, flags, 2 * K - 1, seed, chain_offset, 2,
+                                                             TAG_AIS, betas_dev, wpart, sm_count, st))) return rc;
     ais_reduce_kernel<<<(unsigned)ceil_div64(M, 256), 256, 0, st>>>(wpart, pl.wpart_ld, M, logw);
     return check_launch("ais_reduce_kernel");
   }

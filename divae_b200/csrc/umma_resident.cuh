@@ -1,0 +1,626 @@
+// Resident kernel: priors up to 512 x 512 with W held in shared memory and the chain states kept on the chip for ALL
+// half-steps of a block-Gibbs (or AIS) call.  (BASELINE configs[4]: AIS of a 512 x 512 prior; also few chains on
+// 256 x 256 ... 512 x 512 priors, where a half-step is bound by its dependency latency, not by the tensor pipe.)
+//
+// A thread-block CLUSTER of C = units / 64 CTAs (<= 8) owns one 128-chain row block - or two, ping-pong - for the whole
+// schedule.  CTA j computes the 64 output units [64 j, 64 j + 64) of every half-step:
+//   * its two W slices stay in shared memory for the life of the kernel (loaded once by TMA):
+//       direction 0 (v -> h): W[:, 64j : 64j+64]  as K blocks of [64 k x 64 n], MN-major B operand
+//       direction 1 (h -> v): W[64j : 64j+64, :]  as K blocks of [64 n x 64 k], K-major B operand
+//     (2 x 64 KB at 512 x 512 - there is no W traffic at all after the prologue);
+//   * the states travel between the CTAs as BIT WORDS over distributed shared memory: an epilogue lane owns one chain
+//     (one TMEM lane) and 32 units, i.e. exactly one 32-bit word, which it writes into every consumer CTA with
+//     st.async (... mbarrier::complete_tx): 8 KB per CTA and half-step instead of the 128 KB bf16 tile, no global
+//     memory, no flags, no polling - the consumer's mbarrier completes when the bytes have landed;
+//   * expander warps turn the words of one K block (128 chains x 64 units) into the SWIZZLE_128B bf16 A tile the
+//     tensor core reads, with one 16-byte table lookup per 8 units (a 4 KB table of the 256 byte patterns), into a
+//     3-stage ring; the MMA warp issues tcgen05.mma (M = 128, N = 64) as the K blocks appear;
+//   * the epilogue (tcgen05.ld -> bias, sigmoid, Philox, Bernoulli compare: the same arithmetic and draw contract as
+//     umma_common.cuh:epilogue_tile, so every kernel draws the same chains) produces the next words.
+// With two row blocks per cluster (ping-pong, two TMEM accumulators) the MMAs and the expansion of one block overlap
+// the epilogue of the other; with one the kernel runs at the latency of a single dependent half-step.
+// Clusters are independent of each other (chains are independent), so they need not be co-resident.
+#pragma once
+#include "umma_chain.cuh"
+
+namespace rbm {
+namespace {
+
+constexpr int kResBN = 64;                 // output units per CTA and direction
+constexpr int kResStages = 3;              // A ring
+constexpr int kResEpiWarps = 8;            // warps 4..11: 4 TMEM lane quarters x 2 column sets of 32 units
+constexpr int kResExpWarps = 8;            // warps 12..19
+constexpr int kResThreads = 32 * (4 + kResEpiWarps + kResExpWarps);
+constexpr int kResMaxTiles = 8;            // portable cluster size
+constexpr int kResWBlockBytes = BLOCK_K * kResBN * 2;        // 8 KB: one K block of a W slice
+constexpr int kResBitsBytes = kResMaxTiles * 2 * BLOCK_M * 4;   // 8 KB: the words of one (slot, parity)
+constexpr int kResTableBytes = 256 * 16;
+
+struct ResidentArgs {
+  const float* nbias[2];   // [dir]: -log2(e) * bias of the units WRITTEN by dir (0: hidden, 1: visible), zero padded
+  int n_valid[2];          // real unit count written by dir
+  int n_tiles[2];          // 64-unit tiles written by dir (= K blocks READ by the other direction)
+  int ld[2];               // padded unit count (row pitch) of the state written by dir
+  int row_blocks;          // 128-chain blocks
+  int slots;               // 1 or 2 row blocks per cluster in flight
+  int steps;               // half-steps, starting with direction 0
+  uint64_t seed, chain_offset, step_offset;
+  uint32_t tag;
+  const float* betas;      // annealed flavours: beta index of half-step t is 1 + t/2
+  float* wpart;            // AIS: [rows, wpart_ld] log-weight partials (log2 units), one slot per 32 hidden units
+  int wpart_ld;
+  uint32_t kf_magic;
+  const __nv_bfloat16* v_init;   // [rows_pad, ld[1]] initial visible state ({0,1} bf16)
+  __nv_bfloat16* out[2];         // final states: out[0] = hidden [rows_pad, ld[0]], out[1] = visible [rows_pad, ld[1]]
+};
+
+constexpr int kResStageBytes = 2 * 2 * kResEpiWarps * 128;   // [slot][use parity][epilogue warp][32 words]
+constexpr int kResPrologueBytes = 2 * kResExpWarps * 128;       // [slot][expander warp][32 words]
+
+// Latency tracing (debug builds only: RBM_B200_NVCC_DEFS=-DRBM_RES_TRACE): SM clock of the key events of a few
+// half-steps of CTA 0, read back through rbm_b200_debug_resident_trace().
+#ifdef RBM_RES_TRACE
+__device__ unsigned long long g_res_trace[64 * 16];
+#define RES_TRACE(ev, t, cond)                                                                       \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && (cond) && (t) >= 200 && (t) < 216) g_res_trace[((t) - 200) * 64 + (ev)] = clock64(); \
+  } while (0)
+#else
+#define RES_TRACE(ev, t, cond) do { } while (0)
+#endif
+
+struct ResidentSmem {
+  uint32_t w0, w1, ring, table, bits, stage, pro, bars;
+  int total;
+};
+__host__ __device__ inline ResidentSmem resident_smem(int tiles_h, int tiles_v) {
+  ResidentSmem s;
+  s.w0 = 0;                                                  // K blocks of direction 0 = visible tiles
+  s.w1 = s.w0 + (uint32_t)tiles_v * kResWBlockBytes;          // K blocks of direction 1 = hidden tiles
+  s.ring = s.w1 + (uint32_t)tiles_h * kResWBlockBytes;
+  s.table = s.ring + kResStages * kABytes;
+  s.bits = s.table + kResTableBytes;
+  s.stage = s.bits + 4 * kResBitsBytes;                       // bits: [slot][parity]
+  s.pro = s.stage + kResStageBytes;
+  s.bars = s.pro + kResPrologueBytes;
+  s.total = (int)s.bars + 256 + 1024;
+  return s;
+}
+
+// bulk copy shared::cta -> shared::cluster (any CTA of the cluster, this one included); the destination CTA's mbarrier
+// receives ONE complete_tx of `bytes` when the data has landed
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t cluster_dst, uint32_t cta_src, uint32_t bytes, uint32_t cluster_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(cluster_dst), "r"(cta_src), "r"(bytes), "r"(cluster_bar) : "memory");
+}
+// generic-mode PRMT: selector nibble bit 3 replicates the sign bit of the selected byte over the whole byte
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// mbarrier wait with a suspend-time hint: the waits of this kernel are long (a dependent half-step away) and every
+// spin of a waiting warp takes an issue slot from the expander / epilogue warps
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!done);
+}
+
+// One epilogue warp, one half-step of one row block: 32 chains (lanes) x 32 units -> one 32-bit word per lane.
+// Same arithmetic as epilogue_tile (umma_common.cuh): arg = acc * scale + nbias * bmul, s = 1 + 2^arg,
+// d = 65536 - k16 s; fire iff d >= s; 0 <= d < s is re-done on the exact path.
+template <int EPI, class WaitFn, class ReleaseFn>
+__device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint32_t tmem_acc, int col0, uint32_t chain,
+                                                      int quarter, int cq, int lane, float& wsum, WaitFn wait_full,
+                                                      ReleaseFn release) {
+  uint32_t w[4][4];
+  const uint32_t blk0 = (uint32_t)(col0 >> 5) * 4u;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const uint4 x = draw_block(ep.ctx, blk0 + b, chain);
+    w[b][0] = x.x; w[b][1] = x.y; w[b][2] = x.z; w[b][3] = x.w;
+  }
+  wait_full();
+  tcgen05_fence_after();
+  uint32_t bits = 0;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t r[16];
+    tmem_ld16(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cq * 32 + 16 * hh), r);
+    tmem_ld_wait();
+    if (hh == 1) {
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) release();
+    }
+    uint32_t amb = 0;          // units whose 16-bit field alone cannot decide (probability 2^-16 per draw)
+    uint32_t half_bits = 0;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const float4 nb4 = __ldg(reinterpret_cast<const float4*>(ep.nbias + col0 + 16 * hh) + q4);
+      const float nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        const int c16 = 4 * q4 + i4;
+        const int cc = 16 * hh + c16;
+        const int b = (cc & 7) >> 1;
+        const int slot = 2 * (cc >> 3) + (cc & 1);
+        const uint32_t word = w[b][slot >> 1];
+        const uint32_t mbits = (slot & 1) ? __byte_perm(word, ep.kf_magic, 0x7632) : __byte_perm(word, ep.kf_magic, 0x7610);
+        const float kf = __uint_as_float(mbits) - 8388608.0f;
+        const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbv[i4])
+                                           : fmaf(__uint_as_float(r[c16]), ep.scale, nbv[i4] * ep.bmul);
+        const Decision q = decision_terms(arg, kf);
+        if (EPI == EPI_AIS_WEIGHT) {
+          const float ak = fminf(arg, 80.0f);
+          const float akm1 = ak * ep.ratio;
+          if (col0 + cc < ep.n_valid)
+            wsum += (akm1 - ak) + lg2_approx(fminf(q.s, 1.2089258e24f)) - lg2_approx(1.0f + ex2_approx(akm1));
+        }
+        if (q.d >= q.s) half_bits |= 1u << c16;
+        if (__float_as_uint(q.d) < __float_as_uint(q.s)) amb |= 1u << c16;
+      }
+    }
+    if (amb) {
+      // Only the ambiguous units go through the exact path (for every other unit it returns what the fast path
+      // decided): in this kernel a whole cluster waits for its slowest warp every half-step, so the rare path
+      // must stay short.
+#pragma unroll
+      for (int c16 = 0; c16 < 16; ++c16) {
+        if ((amb >> c16) & 1u) {
+          const int cc = 16 * hh + c16;
+          const int b = (cc & 7) >> 1, slot = 2 * (cc >> 3) + (cc & 1);
+          const uint32_t word = w[b][slot >> 1];
+          const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
+          const float nbx = __ldg(ep.nbias + col0 + cc);
+          const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbx)
+                                             : fmaf(__uint_as_float(r[c16]), ep.scale, nbx * ep.bmul);
+          const uint32_t one = resolve_exact(arg, k16, ep.ctx, blk0 + b, chain, (uint32_t)slot);
+          half_bits = (half_bits & ~(1u << c16)) | (one << c16);
+        }
+      }
+    }
+    bits |= half_bits << (16 * hh);
+  }
+  return bits;
+}
+
+template <int EPI0, int EPI1>
+__global__ void __launch_bounds__(kResThreads, 1)
+umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const ResidentSmem L = resident_smem(args.n_tiles[0], args.n_tiles[1]);
+  const uint32_t bar_base = smem_base + L.bars;
+  const uint32_t w_full = bar_base;
+  auto ring_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto ring_empty = [&](int s) { return bar_base + 8u * (1 + kResStages + s); };
+  auto tmem_full = [&](int s) { return bar_base + 8u * (1 + 2 * kResStages + s); };
+  auto tmem_empty = [&](int s) { return bar_base + 8u * (3 + 2 * kResStages + s); };
+  auto bits_full = [&](int s, int par) { return bar_base + 8u * (5 + 2 * kResStages + 2 * s + par); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bars + 8 * (9 + 2 * kResStages));
+  auto bits_addr = [&](int s, int par, int word, int row) {
+    return smem_base + L.bits + (uint32_t)(((s * 2 + par) * 16 + word) * BLOCK_M + row) * 4u;
+  };
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t csize;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  const int C = (int)csize;
+  const int j = (int)cluster_ctarank();
+  const int cluster_id = (int)blockIdx.x / C, n_clusters = (int)gridDim.x / C;
+  // (scalars and selects instead of arrays indexed by the direction: run-time indexing would put them, and the
+  //  whole argument struct, into local memory)
+  const bool act0 = j < args.n_tiles[0], act1 = j < args.n_tiles[1];     // this CTA computes units of direction 0 / 1
+  const int nkb0 = args.n_tiles[1], nkb1 = args.n_tiles[0];              // K blocks read by direction 0 / 1
+  constexpr uint32_t kTmemCols = 2 * kResBN;
+  const int n_pairs = ceil_div(ceil_div(args.row_blocks, args.slots), n_clusters);   // upper bound, same for every cluster
+
+  if (warp_idx == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+  if (warp_idx == 1 && lane == 0) {
+    mbar_init(w_full, 1);
+    for (int s = 0; s < kResStages; ++s) { mbar_init(ring_full(s), kResExpWarps / 2); mbar_init(ring_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), kResEpiWarps);
+      for (int par = 0; par < 2; ++par) {
+        mbar_init(bits_full(s, par), 1);
+        // armed for its first use: the words of all K blocks of the direction that reads this parity
+        mbar_arrive_expect_tx(bits_full(s, par), (uint32_t)(par ? nkb1 : nkb0) * 2u * BLOCK_M * 4u);
+      }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp_idx == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < 256) {
+    // byte pattern -> eight bf16 {0,1}: unit i of the byte is element i of the 16-byte chunk
+    const uint32_t b = threadIdx.x;
+    uint32_t e[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) e[p] = (((b >> (2 * p)) & 1u) ? 0x3F80u : 0u) | (((b >> (2 * p + 1)) & 1u) ? 0x3F800000u : 0u);
+    st_shared_v4(smem_base + L.table + b * 16u, e[0], e[1], e[2], e[3]);
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // row block of (pair, slot) for this cluster, or -1
+  auto row_block = [&](int pair, int s) {
+    const int item = (pair * n_clusters + cluster_id) * args.slots + s;
+    return (s < args.slots && item < args.row_blocks) ? item : -1;
+  };
+
+  if (warp_idx == 0) {
+    // ============================ W slices: loaded once ============================
+    if (lane == 0) {
+      const uint32_t bytes = (act0 ? (uint32_t)nkb0 : 0u) * kResWBlockBytes + (act1 ? (uint32_t)nkb1 : 0u) * kResWBlockBytes;
+      if (bytes != 0u) {
+        mbar_arrive_expect_tx(w_full, bytes);
+        if (act0)
+          for (int kb = 0; kb < nkb0; ++kb)     // W[64 kb .. +64 (v, k)][64 j .. +64 (h, n)]
+            tma_load_2d(smem_base + L.w0 + kb * kResWBlockBytes, &tm_w, w_full, j * kResBN, kb * BLOCK_K);
+        if (act1)
+          for (int kb = 0; kb < nkb1; ++kb)     // W[64 j .. +64 (v, n)][64 kb .. +64 (h, k)]
+            tma_load_2d(smem_base + L.w1 + kb * kResWBlockBytes, &tm_w, w_full, kb * BLOCK_K, j * kResBN);
+      } else {
+        mbar_arrive(w_full);
+      }
+    }
+    __syncwarp();
+    for (int pair = 0; pair < n_pairs; ++pair) cluster_sync_all();
+  } else if (warp_idx == 1) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc0 = make_idesc(BLOCK_M, kResBN, true);    // dir 0: B MN-major
+    constexpr uint32_t idesc1 = make_idesc(BLOCK_M, kResBN, false);   // dir 1: B K-major
+    mbar_wait(w_full, 0);
+    int stage = 0; uint32_t phase = 0;
+    uint32_t uses[2] = {0u, 0u};
+    const uint64_t adesc_base = make_smem_desc(smem_base + L.ring, 16, 1024);            // A: K-major
+    const uint64_t bdesc0_base = make_smem_desc(smem_base + L.w0, BLOCK_K * 128, 1024);  // dir 0: MN-major
+    const uint64_t bdesc1_base = make_smem_desc(smem_base + L.w1, 16, 1024);             // dir 1: K-major
+    for (int pair = 0; pair < n_pairs; ++pair) {
+      for (int t = 0; t < args.steps; ++t) {
+        const int dir = t & 1;
+        const int nkb = dir ? nkb1 : nkb0;
+        if (dir ? act1 : act0) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (row_block(pair, s) < 0) continue;
+            mbar_wait(tmem_empty(s), (uses[s] & 1u) ^ 1u);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(s * kResBN);
+            // Descriptors advance by ADDING to the 14-bit address field (all shared-memory addresses are below 256 KB, so
+            // nothing carries out of it): ~35 instructions per K block instead of ~100 of descriptor arithmetic - with
+            // 64-wide tiles a K block is only ~130 cycles of tensor time, the issue loop must not be longer.
+            uint64_t bdesc = dir ? bdesc1_base : bdesc0_base;
+            const uint64_t bstep = dir ? (uint64_t)((UMMA_K * 2) >> 4) : (uint64_t)((UMMA_K * 128) >> 4);
+            const uint32_t idesc = dir ? idesc1 : idesc0;
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(ring_full(stage), phase);
+              tcgen05_fence_after();
+              RES_TRACE(10 + kb, t, lane == 0 && s == 0);
+              if (elect_one_sync()) {
+                const uint64_t adesc = adesc_base + (uint64_t)(stage * (kABytes >> 4));
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                  umma_bf16(tmem_d, adesc + (uint64_t)(k * ((UMMA_K * 2) >> 4)), bdesc + (uint64_t)k * bstep, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_commit(ring_empty(stage));
+              }
+              __syncwarp();
+              bdesc += (uint64_t)(kResWBlockBytes >> 4);
+              if (++stage == kResStages) { stage = 0; phase ^= 1u; }
+            }
+            if (elect_one_sync()) umma_commit(tmem_full(s));
+            __syncwarp();
+            RES_TRACE(18, t, lane == 0 && s == 0);
+            ++uses[s];
+          }
+        }
+      }
+      cluster_sync_all();
+    }
+  } else if (warp_idx >= 4 && warp_idx < 4 + kResEpiWarps) {
+    // ================================= epilogue =================================
+    const int quarter = warp_idx & 3;
+    const int cq = (warp_idx - 4) >> 2;
+    const int row_in_blk = quarter * 32 + lane;
+    uint32_t uses[2] = {0u, 0u};
+    for (int pair = 0; pair < n_pairs; ++pair) {
+      float wsum[2] = {0.f, 0.f};
+      for (int t = 0; t < args.steps; ++t) {
+        const int dir = t & 1;
+        if (dir ? act1 : act0) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int rb = row_block(pair, s);
+            if (rb < 0) continue;
+            const int row = rb * BLOCK_M + row_in_blk;
+            const uint32_t chain = (uint32_t)(args.chain_offset + (uint64_t)row);
+            const int col0 = j * kResBN + cq * 32;
+            EpiParams ep;
+            ep.nbias = dir ? args.nbias[1] : args.nbias[0]; ep.ldo = dir ? args.ld[1] : args.ld[0];
+            ep.n_valid = dir ? args.n_valid[1] : args.n_valid[0];
+            ep.ctx = make_draw_ctx(args.seed, args.step_offset + (uint64_t)t, args.tag);
+            ep.scale = -1.4426950408889634f; ep.bmul = 1.f; ep.ratio = 0.f; ep.debug_mode = 0;
+            ep.kf_magic = args.kf_magic;
+            if (EPI0 != EPI_GIBBS) {
+              const float bk = __ldg(args.betas + 1 + (t >> 1)), bkm1 = __ldg(args.betas + (t >> 1));
+              ep.scale = -1.4426950408889634f * bk;
+              ep.bmul = dir == 0 ? bk : 1.f;
+              ep.ratio = bkm1 / bk;
+            }
+            const uint32_t par_full = uses[s] & 1u;
+            auto wait_full = [&] { mbar_wait_long(tmem_full(s), par_full); RES_TRACE(20 + 4 * (warp_idx == 11), t, lane == 0 && s == 0 && (warp_idx == 4 || warp_idx == 11)); };
+            auto release = [&] { mbar_arrive(tmem_empty(s)); RES_TRACE(21 + 4 * (warp_idx == 11), t, s == 0 && (warp_idx == 4 || warp_idx == 11)); };
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(s * kResBN);
+            uint32_t bits;
+            float wstep = 0.f;      // this half-step's 32-unit sum is added as ONE term, like the chain kernel's red
+            if (dir == 0) bits = resident_epilogue<EPI0>(ep, tmem_acc, col0, chain, quarter, cq, lane, wstep, wait_full, release);
+            else bits = resident_epilogue<EPI1>(ep, tmem_acc, col0, chain, quarter, cq, lane, wstep, wait_full, release);
+            wsum[s] += wstep;
+            __syncwarp();
+            RES_TRACE(22 + 4 * (warp_idx == 11), t, lane == 0 && s == 0 && (warp_idx == 4 || warp_idx == 11));
+            if (t + 1 < args.steps) {
+              // This warp's 32 words (32 chains x 32 units) go to every CTA that computes the next half-step: staged in
+              // local shared memory, then ONE 128-byte bulk copy per destination (one complete_tx on its barrier;
+              // per-lane st.async cost 256 barrier updates per CTA pair and half-step and serialised on the barrier).
+              // The staging slot alternates with the use count: the copy issued two uses ago has been consumed.
+              const int par = (t + 1) & 1;
+              const uint32_t stg = smem_base + L.stage + (uint32_t)(((s * 2 + (int)(uses[s] & 1u)) * kResEpiWarps + (warp_idx - 4)) * 128);
+              st_shared_u32(stg + (uint32_t)lane * 4u, bits);
+              fence_proxy_async_smem();
+              __syncwarp();
+              {
+                // lane d serves destination CTA d
+                const uint32_t dst = bits_addr(s, par, 2 * j + cq, quarter * 32);
+                const uint32_t bar = bits_full(s, par);
+                const int n_dst = dir ? args.n_tiles[0] : args.n_tiles[1];
+                if (lane < n_dst) dsmem_bulk_copy(mapa_u32(dst, (uint32_t)lane), stg, 128u, mapa_u32(bar, (uint32_t)lane));
+              }
+              __syncwarp();
+              RES_TRACE(23 + 4 * (warp_idx == 11), t, lane == 0 && s == 0 && (warp_idx == 4 || warp_idx == 11));
+            }
+            ++uses[s];
+            if (t + 2 >= args.steps) {
+              // final (v, h) of the call: bf16 {0,1} into the state tiles the rest of the library reads
+              uint4* o = reinterpret_cast<uint4*>((dir ? args.out[1] : args.out[0]) + (size_t)row * (dir ? args.ld[1] : args.ld[0]) + col0);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t by = (bits >> (8 * c)) & 0xFFu;
+                o[c] = ld_shared_v4(smem_base + L.table + by * 16u);
+              }
+            }
+          }
+        }
+      }
+      if (EPI0 == EPI_AIS_WEIGHT && act0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int rb = row_block(pair, s);
+          if (rb < 0) continue;
+          const int row = rb * BLOCK_M + row_in_blk;
+          atomicAdd(args.wpart + (size_t)row * args.wpart_ld + ((j * kResBN + cq * 32) >> 5), wsum[s]);
+        }
+      }
+      __syncwarp();
+      cluster_sync_all();
+    }
+  } else if (warp_idx >= 4 + kResEpiWarps) {
+    // ================================ expanders ================================
+    const int e = warp_idx - 4 - kResEpiWarps;
+    const int row = (e & 3) * 32 + lane;       // chain within the row block
+    const int half = e >> 2;                   // prologue: which 32 units of this CTA's 64; main loop: expander group
+    const bool armer = (e == 0 && lane == 0);
+    int stage = 0; uint32_t phase = 0;
+    uint32_t bphase = 0;                       // bit (2 s + par): phase parity of bits_full(s, par) to wait for
+    for (int pair = 0; pair < n_pairs; ++pair) {
+      // prologue: this CTA's 64 units of the initial visible state -> words for the CTAs that compute direction 0
+      if (act1) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int rb = row_block(pair, s);
+          if (rb < 0) continue;
+          const uint4* src = reinterpret_cast<const uint4*>(args.v_init + (size_t)(rb * BLOCK_M + row) * args.ld[1] + j * kResBN + half * 32);
+          uint32_t bits = 0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 q = __ldg(src + c);
+            const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              if (wds[p] & 0x0000FFFFu) bits |= 1u << (8 * c + 2 * p);
+              if (wds[p] & 0xFFFF0000u) bits |= 1u << (8 * c + 2 * p + 1);
+            }
+          }
+          const uint32_t stg = smem_base + L.pro + (uint32_t)((s * kResExpWarps + e) * 128);
+          st_shared_u32(stg + (uint32_t)lane * 4u, bits);
+          fence_proxy_async_smem();
+          __syncwarp();
+          {
+            const uint32_t dst = bits_addr(s, 0, 2 * j + half, (e & 3) * 32);
+            const uint32_t bar = bits_full(s, 0);
+            if (lane < args.n_tiles[0]) dsmem_bulk_copy(mapa_u32(dst, (uint32_t)lane), stg, 128u, mapa_u32(bar, (uint32_t)lane));
+          }
+          __syncwarp();
+        }
+      }
+      for (int t = 0; t < args.steps; ++t) {
+        const int dir = t & 1, par = t & 1;
+        const int nkb = dir ? nkb1 : nkb0;
+        if (dir ? act1 : act0) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (row_block(pair, s) < 0) continue;
+            const uint32_t bit = 1u << (2 * s + par);
+            {
+              // the first ring slots of this half-step are normally free long before its words arrive: wait for them
+              // first, off the critical path
+              int st2 = stage; uint32_t ph2 = phase;
+              for (int kb = 0; kb < nkb && kb < kResStages; ++kb) {
+                if ((kb & 1) == half) mbar_wait(ring_empty(st2), ph2 ^ 1u);
+                if (++st2 == kResStages) { st2 = 0; ph2 ^= 1u; }
+              }
+            }
+            mbar_wait_long(bits_full(s, par), (bphase & bit) ? 1u : 0u);
+            bphase ^= bit;
+            RES_TRACE(0, t, e == 0 && lane == 0 && s == 0);
+            // re-arm for the next use of this (slot, parity): same direction, same byte count
+            if (armer) mbar_arrive_expect_tx(bits_full(s, par), (uint32_t)nkb * 2u * BLOCK_M * 4u);
+            // Two groups of four warps expand alternate K blocks concurrently (the expansion of a K block is a
+            // dependent chain of ~450 cycles: word load, PRMTs, stores, proxy fence, arrive); a warp covers 32
+            // chains x 64 units = both words of its rows.
+            for (int kb = 0; kb < nkb; ++kb) {
+              if ((kb & 1) == half) {
+                const uint32_t word0 = ld_shared_u32(bits_addr(s, par, 2 * kb, row));
+                const uint32_t word1 = ld_shared_u32(bits_addr(s, par, 2 * kb + 1, row));
+                if (kb >= kResStages) mbar_wait(ring_empty(stage), phase ^ 1u);   // (first slots: checked before the words came)
+                const uint32_t arow = smem_base + L.ring + stage * kABytes + (uint32_t)row * 128u;
+#pragma unroll
+                for (int hw = 0; hw < 2; ++hw) {
+                  // 32 units -> 32 bf16 {0,1} in registers: vv[i] = word << (7 - i) carries unit 8c + i in the sign bit
+                  // of byte c; PRMT in sign-replicate mode turns two such bytes into the masks of a bf16 pair, AND
+                  // 0x3F80 (2.5 ALU instructions per pair; a 256-entry table lookup cost a 10-way bank conflict)
+                  const uint32_t word = hw ? word1 : word0;
+                  uint32_t vv[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) vv[i] = word << (7 - i);
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int pp = 0; pp < 4; ++pp) {
+                      const uint32_t sel = (uint32_t)((8 | c) | ((8 | c) << 4) | ((12 | c) << 8) | ((12 | c) << 12));
+                      o[pp] = prmt_b32(vv[2 * pp], vv[2 * pp + 1], sel) & 0x3F803F80u;
+                    }
+                    st_shared_v4(arow + ((((uint32_t)(hw * 4 + c)) ^ ((uint32_t)row & 7u)) << 4), o[0], o[1], o[2], o[3]);
+                  }
+                }
+                fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ring_full(stage));
+                RES_TRACE(1 + kb, t, (e & 3) == 0 && lane == 0 && s == 0);
+              }
+              if (++stage == kResStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      cluster_sync_all();
+    }
+  } else {
+    // warps 2, 3: only the pair barriers
+    for (int pair = 0; pair < n_pairs; ++pair) cluster_sync_all();
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp_idx == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+inline int res_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Shapes the resident kernel covers: both sides fit 8 tiles of 64 units (W slices 2 x 64 KB at most).
+inline bool resident_supported(int nVp, int nHp) { return nVp <= kResMaxTiles * kResBN && nHp <= kResMaxTiles * kResBN; }
+
+// Clusters of `cluster` CTAs of the resident kernel that fit on the device at once (GPC boundaries make this less than
+// sm_count / cluster: 15 clusters of 8 on a 148-SM B200).  Queried once per (flavour, cluster size, shared-memory size).
+template <int EPI0, int EPI1>
+int resident_max_clusters(int cluster, int smem_bytes, int sm_count, int* out) {
+  static int cache[9][8] = {};   // [cluster size][smem size in 32 KB steps], 0 = not queried
+  auto kern = umma_resident_kernel<EPI0, EPI1>;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  if ((rc = ensure_dynamic_smem(kern, di.device, smem_bytes))) return rc;
+  int& slot = cache[cluster][std::min(7, smem_bytes >> 15)];
+  if (slot == 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(kResThreads);
+    cfg.gridDim = dim3((unsigned)cluster);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+      (void)cudaGetLastError();
+      n = std::max(1, sm_count / cluster / 2);
+    }
+    slot = n;
+  }
+  *out = slot;
+  return 0;
+}
+
+inline int resident_cluster_size(int tiles_h, int tiles_v) {
+  const int tiles = std::max(tiles_h, tiles_v);
+  return tiles <= 1 ? 1 : tiles <= 2 ? 2 : tiles <= 4 ? 4 : 8;
+}
+
+template <int EPI0, int EPI1>
+int launch_resident(const CUtensorMap& tm_w, ResidentArgs a, int cluster, int sm_count, cudaStream_t st) {
+  auto kern = umma_resident_kernel<EPI0, EPI1>;
+  const ResidentSmem L = resident_smem(a.n_tiles[0], a.n_tiles[1]);
+  int max_clusters = 0;
+  int rc = resident_max_clusters<EPI0, EPI1>(cluster, L.total, sm_count, &max_clusters);
+  if (rc) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kResThreads);
+  cfg.dynamicSmemBytes = (size_t)L.total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static const int force_slots = res_env_int("RBM_B200_RESIDENT_SLOTS", 0);
+  // one row block per cluster while there are clusters to spare (latency), two in ping-pong otherwise (throughput)
+  a.slots = force_slots == 1 || force_slots == 2 ? force_slots : (a.row_blocks > max_clusters ? 2 : 1);
+  const int items = ceil_div(a.row_blocks, a.slots);
+  const int rounds = ceil_div(items, max_clusters);
+  const int n_clusters = ceil_div(items, rounds);
+  cfg.gridDim = dim3((unsigned)(n_clusters * cluster));
+  RBM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm_w, a));
+  return check_launch("umma_resident_kernel");
+}
+
+}  // namespace
+}  // namespace rbm
