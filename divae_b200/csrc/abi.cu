@@ -89,7 +89,9 @@ int pick_variant(const rbm_b200_params* p, int64_t B, int variant) {
   const int nmax = p->n_visible > p->n_hidden ? p->n_visible : p->n_hidden;
   // (the bf16 kernels round the fp32 W themselves when no bf16 copy is handed in)
   if (smem_variant_supported(p->n_visible, p->n_hidden) && (nmax <= 128 || B < 8192)) return RBM_B200_VARIANT_SMEM;
-  if (umma_variant_supported(p->n_visible, p->n_hidden) && B >= 128) return RBM_B200_VARIANT_UMMA;
+  // Any chain count: a shard of a few chains must sample with the same bf16-rounded W as the job it belongs to
+  // (the GENERAL path keeps W in fp32), see divae_b200/dist.py.
+  if (umma_variant_supported(p->n_visible, p->n_hidden) && B >= 1) return RBM_B200_VARIANT_UMMA;
   if (smem_variant_supported(p->n_visible, p->n_hidden)) return RBM_B200_VARIANT_SMEM;
   return RBM_B200_VARIANT_GENERAL;
 }
@@ -154,6 +156,17 @@ size_t rbm_b200_block_gibbs_workspace(int32_t n_visible, int32_t n_hidden, int64
   }
 }
 
+size_t rbm_b200_block_gibbs_stats_workspace(int32_t n_visible, int32_t n_hidden, int64_t B, int variant) {
+  if (B <= 0 || n_visible <= 0 || n_hidden <= 0) return 0;
+  rbm_b200_params q{};
+  q.n_visible = n_visible; q.n_hidden = n_hidden;
+  switch (pick_variant(&q, B, variant)) {
+    case RBM_B200_VARIANT_UMMA: return umma_workspace_bytes(n_visible, n_hidden, B);
+    case RBM_B200_VARIANT_SMEM: return smem_stats_workspace_bytes(n_visible, n_hidden, B);
+    default: return 0;
+  }
+}
+
 int64_t rbm_b200_block_gibbs_launch_count(int32_t n_visible, int32_t n_hidden, int64_t B, int32_t k, int variant) {
   if (B <= 0 || n_visible <= 0 || n_hidden <= 0 || k < 0) return 0;
   if (require_device()) return -1;
@@ -183,7 +196,11 @@ static int block_gibbs_impl(const rbm_b200_params* p, float* v, float* h, int64_
   const int chosen = pick_variant(p, B, variant);
   if (chosen == RBM_B200_VARIANT_SMEM) {
     RBM_REQUIRE(p->W_bf16 || p->W, RBM_B200_ERR_INVALID, "SMEM variant needs W (fp32) or W_bf16");
-    const bool fuse = S_vh != nullptr && k > 0 && smem_can_fuse_stats(p->n_visible, p->n_hidden);
+    // up to 64 units: counted inside the sampling kernel; 65 - 256 units: tensor-core GEMM over the bf16 state tiles the
+    // final sweep leaves in the workspace (without a workspace: fp32 SIMT statistics of the returned states, below)
+    const bool fuse = S_vh != nullptr && k > 0 &&
+                      (smem_can_fuse_stats(p->n_visible, p->n_hidden) ||
+                       (workspace != nullptr && workspace_bytes >= smem_stats_workspace_bytes(p->n_visible, p->n_hidden, B)));
     if (stats_fused) *stats_fused = fuse;
     return smem_block_gibbs(p, v, h, B, k, init_chains, seed, chain_offset, step_offset, workspace,
                             workspace_bytes, st, fuse ? S_vh : nullptr, fuse ? S_v : nullptr, fuse ? S_h : nullptr);

@@ -51,6 +51,11 @@ struct SmemArgs {
   float* S_vh;           // [nV, nH]
   float* S_v;            // [nV]
   float* S_h;            // [nH]
+  // optional bf16 {0,1} copies of the final states, [B, ld16v] / [B, ld16h] (ld = units rounded up to 64): written from the
+  // on-chip state words in the final sweep and read by the tensor-core statistics GEMM for priors of 65 - 256 units
+  uint16_t* v16;
+  uint16_t* h16;
+  int ld16v, ld16h;
 };
 
 constexpr int kStatLd = 72;   // bf16 row pitch of the per-warp [16 chains x 64 units] statistics tiles (+16 B pad)
@@ -364,6 +369,8 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
       for (int side = 0; side < 2; ++side) {
         const uint32_t* bits = side ? myh : myv;
         float* out = side ? args.h : args.v;
+        uint16_t* out16 = side ? args.h16 : args.v16;
+        const int ld16 = side ? args.ld16h : args.ld16v;
         const int n = side ? nH : nV;
         const int wb = side ? h_begin : v_begin, we = side ? h_end : v_end;
         if (side == 1 && args.k == 0) continue;
@@ -380,6 +387,8 @@ __global__ void __launch_bounds__(256, 1) smem_gibbs_kernel(const SmemArgs args)
                 const float f1 = (word >> state_bit(j, rowhalf, 1)) & 1u ? 1.f : 0.f;
                 if (unit < n) out[r * n + unit] = f0;
                 if (unit + 1 < n) out[r * n + unit + 1] = f1;
+                if (out16 != nullptr)   // (units beyond n inside the last word are 0: K padding of the half-steps)
+                  *reinterpret_cast<uint32_t*>(out16 + r * ld16 + unit) = (f0 != 0.f ? 0x3F80u : 0u) | (f1 != 0.f ? 0x3F800000u : 0u);
               }
             }
         }
@@ -482,10 +491,17 @@ bool smem_variant_supported(int nV, int nH) { return nV >= 1 && nH >= 1 && nV <=
 
 size_t smem_workspace_bytes(int, int, int64_t) { return 0; }
 
+// Workspace of a call WITH statistics: bf16 copies of the final states for the tensor-core statistics of priors with
+// 65 - 256 units per side (up to 64 units the statistics are accumulated inside the sampling kernel: nothing needed)
+size_t smem_stats_workspace_bytes(int nV, int nH, int64_t B) {
+  if (smem_can_fuse_stats(nV, nH) || B <= 0) return 0;
+  return (size_t)B * (size_t)(round_up(nV, 64) + round_up(nH, 64)) * 2 + 256;
+}
+
 bool smem_can_fuse_stats(int nV, int nH) { return nV <= 64 && nH <= 64; }
 
 int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains, uint64_t seed,
-                     uint64_t chain_offset, uint64_t step_offset, void*, size_t, cudaStream_t st, float* S_vh,
+                     uint64_t chain_offset, uint64_t step_offset, void* ws, size_t ws_bytes, cudaStream_t st, float* S_vh,
                      float* S_v, float* S_h) {
   RBM_REQUIRE(smem_variant_supported(p->n_visible, p->n_hidden), RBM_B200_ERR_UNSUPPORTED,
               "SMEM variant supports priors up to %d x %d units, got %d x %d", kMaxUnits, kMaxUnits, p->n_visible,
@@ -500,6 +516,17 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
   a.seed = seed; a.chain_offset = chain_offset; a.step_offset = step_offset;
   const bool fuse = S_vh != nullptr && smem_can_fuse_stats(p->n_visible, p->n_hidden);
   a.S_vh = fuse ? S_vh : nullptr; a.S_v = fuse ? S_v : nullptr; a.S_h = fuse ? S_h : nullptr;
+  // 65 - 256 units: the final sweep also leaves bf16 state tiles in the workspace; <vh>, <v>, <h> are then a tcgen05
+  // GEMM + column sums over those tiles (umma_stats_tiles) instead of an fp32 SIMT pass over the fp32 outputs
+  const bool tiles = S_vh != nullptr && !fuse && k > 0;
+  if (tiles) {
+    RBM_REQUIRE(ws != nullptr && ws_bytes >= smem_stats_workspace_bytes(p->n_visible, p->n_hidden, B), RBM_B200_ERR_WORKSPACE,
+                "SMEM variant with statistics needs %zu bytes of workspace, got %zu",
+                smem_stats_workspace_bytes(p->n_visible, p->n_hidden, B), ws_bytes);
+    a.ld16v = round_up(a.nV, 64); a.ld16h = round_up(a.nH, 64);
+    a.v16 = reinterpret_cast<uint16_t*>(((uintptr_t)ws + 127) & ~(uintptr_t)127);
+    a.h16 = a.v16 + (size_t)B * a.ld16v;
+  }
   const int vwords = ceil_div(a.nV, 64), hwords = ceil_div(a.nH, 64);
   const int maxw = std::max(vwords, hwords);
   const int64_t n_groups = ceil_div64(B, 16);
@@ -524,7 +551,10 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
     int rc = ensure_dynamic_smem(kern, di.device, (int)smem);
     if (rc) return rc;
     kern<<<grid, threads, smem, st>>>(a);
-    return check_launch("smem_gibbs_kernel");
+    if ((rc = check_launch("smem_gibbs_kernel"))) return rc;
+    if (tiles)
+      return umma_stats_tiles(reinterpret_cast<const void*>(a.v16), reinterpret_cast<const void*>(a.h16), B, a.nV, a.nH, S_vh, S_v, S_h, st);
+    return 0;
   };
   if (half) {
     if (maxw == 1) return launch(smem_gibbs_kernel<1, true, true>);

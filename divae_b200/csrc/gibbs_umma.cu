@@ -351,6 +351,9 @@ ChainCfg pick_chain_cfg(int nVp, int nHp, int64_t rows_pad, int sm_count) {
     const int best = std::min(cols(64), std::min(cols(128), cols(256)));
     for (int bn : {256, 128, 64}) {
       if (cols(bn) != best) continue;
+      // small priors (K <= 512: a 256-wide tile is only 8 K blocks deep) with few items run better on 128-wide tiles:
+      // 512^2 at 5,120 - 8,192 chains 8.1 - 8.8 us per half-step against 12.3 (profiles/r02_chain_sweep_512.txt)
+      if (bn == 256 && std::max(nVp, nHp) <= 512 && items(256) < 2 * (int64_t)sm_count) continue;
       c.bn = bn;
       if (items(bn) >= (int64_t)sm_count / 2) break;
     }
@@ -484,6 +487,16 @@ int run_chain(const Plan& pl, uint16_t* Wp, uint16_t* Wlo, const float* nbh, con
   for (int t = 0; t < std::min(steps, 2); ++t) total_items += (int64_t)a.m_groups * a.n_tiles[t & 1];
   if (steps > 2) total_items = (int64_t)1 << 40;
   int grid = sm_count / cfg.ctas;
+  // Fewer items per half-step than clusters: one cluster per item, so that the items a cluster takes one after the other
+  // are always one half-step apart (with 120 - 128 items dealt over 148 CTAs a cluster's next item can sit in the same
+  // half-step as items it depends on, queued behind unfinished work elsewhere: 25 - 35 us per half-step instead of 8
+  // at 512^2, profiles/r02_chain_sweep_512.txt).
+  {
+    const int64_t items_hs = (int64_t)std::min(a.sb_groups, a.m_groups) * std::max(a.n_tiles[0], a.n_tiles[1]);
+    if (items_hs < grid) grid = (int)items_hs;
+    static const int align_grid = env_int("RBM_B200_CHAIN_ALIGN", 0);   // experiment: grid = items / ceil(items / grid)
+    if (align_grid && items_hs < 4 * (int64_t)grid) grid = (int)(items_hs / ceil_div64(items_hs, grid));
+  }
   if (grid_cap > 0) grid = std::min(grid, grid_cap);
   grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, total_items));
   return launch_chain<EPI0, EPI1>(cfg.bn, cfg.ctas, split, tm, a, grid, st);
@@ -581,6 +594,17 @@ namespace rbm {
 bool umma_variant_supported(int nV, int nH) { return nV >= 1 && nH >= 1 && nV <= 16384 && nH <= 16384; }
 
 size_t umma_workspace_bytes(int nV, int nH, int64_t B) { return make_plan(nV, nH, B).total; }
+
+int umma_stats_tiles(const void* v_tiles, const void* h_tiles, int64_t B, int nV, int nH, float* S_vh, float* S_v,
+                     float* S_h, cudaStream_t st) {
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  RBM_REQUIRE(di.cc_major == 10, RBM_B200_ERR_NO_DEVICE, "tensor-core statistics need an sm_100 device (got cc %d.x)", di.cc_major);
+  const Plan pl = make_plan(nV, nH, B);
+  return umma_stats(pl, reinterpret_cast<const __nv_bfloat16*>(v_tiles), reinterpret_cast<const __nv_bfloat16*>(h_tiles), B,
+                    S_vh, S_v, S_h, di.sm_count, st);
+}
 
 // kernels one umma_block_gibbs call launches (no statistics): 3 parameter staging + 1 initial state + chain + 2 outputs
 int64_t umma_launch_count(int nV, int nH, int64_t B, int k, bool split_w) {

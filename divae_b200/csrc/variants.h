@@ -30,6 +30,7 @@ int stats_scale(float* S_vh, float* S_v, float* S_h, int nV, int nH, float scale
 // gibbs_smem.cu — persistent kernel, W (bf16) resident in shared memory
 bool smem_variant_supported(int nV, int nH);
 size_t smem_workspace_bytes(int nV, int nH, int64_t B);
+size_t smem_stats_workspace_bytes(int nV, int nH, int64_t B);   // calls that also return <vh>, <v>, <h>
 // S_vh/S_v/S_h non-null (and smem_can_fuse_stats): raw counts of the final (v,h) are atomically
 // ADDED to them inside the same kernel (caller zeroes before, scales after).
 bool smem_can_fuse_stats(int nV, int nH);
@@ -48,6 +49,11 @@ int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
                      uint64_t seed, uint64_t chain_offset, uint64_t step_offset, void* ws,
                      size_t ws_bytes, cudaStream_t st, float* S_vh = nullptr, float* S_v = nullptr,
                      float* S_h = nullptr, bool split_w = false);
+
+// <vh>, <v>, <h> raw counts of bf16 {0,1} state tiles [B, round_up(nV, 64)] / [B, round_up(nH, 64)], ADDED to the outputs:
+// tcgen05 GEMM V^T H + column sums (the SMEM variant hands its final states over this way for 65 - 256 units)
+int umma_stats_tiles(const void* v_tiles, const void* h_tiles, int64_t B, int nV, int nH, float* S_vh, float* S_v,
+                     float* S_h, cudaStream_t st);
 
 // decoder MLP on generated samples: one tcgen05 GEMM per layer, split-bf16 operands
 size_t umma_decoder_workspace_bytes(const rbm_b200_decoder* d, int64_t B);

@@ -3,6 +3,10 @@
 One process per GPU (torch.distributed, NCCL on GPUs, gloo in CPU tests).  Chains are
 independent given (W, a, c), so the data path has NO collective; because every draw is
 keyed by the GLOBAL chain id, a sharded job draws exactly what the unsharded job would.
+(Kernel choice: `variant="auto"` looks at the LOCAL chain count.  Every choice it can make for a given prior multiplies the
+same bf16-rounded W and follows the same draw contract, so shards and the full job agree except on chains that met a
+draw within 1e-6 of its threshold - the kernels sum in different orders; pass an explicit `variant=` on every rank when
+the shards must be bit-identical slices, as tests/multi_gpu_check.py does.)
 Collectives exist only for
   * the sum-allreduce of the fused negative-phase statistics (one flat buffer), and
   * the log-sum-exp reduction of AIS log-weights (max, then sum of exp).

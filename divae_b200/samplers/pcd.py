@@ -88,10 +88,11 @@ class PCD(BaseSampler):
         if v is None:
             v = torch.empty((B, nV), dtype=torch.float32, device=dev)
         h = torch.empty((B, nH), dtype=torch.float32, device=dev)
-        qkey = (nV, nH, B, self._variant)
+        qkey = (nV, nH, B, self._variant, stats_scale is not None)
         nbytes = self._ws_query.get(qkey)
         if nbytes is None:
-            nbytes = self._ws_query[qkey] = lib.rbm_b200_block_gibbs_workspace(nV, nH, B, self._variant)
+            query = lib.rbm_b200_block_gibbs_stats_workspace if stats_scale is not None else lib.rbm_b200_block_gibbs_workspace
+            nbytes = self._ws_query[qkey] = query(nV, nH, B, self._variant)
         if nbytes and (self._workspace is None or self._workspace.numel() < nbytes
                        or self._workspace.device != dev):
             self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)

@@ -110,6 +110,10 @@ RBM_B200_API int rbm_b200_init_chains(float *v, int64_t B, int32_t n_visible, ui
 /* Bytes of caller-provided workspace rbm_b200_block_gibbs needs for this shape
  * and variant (0 for the GENERAL variant). Host only. */
 RBM_B200_API size_t rbm_b200_block_gibbs_workspace(int32_t n_visible, int32_t n_hidden, int64_t B, int variant);
+/* Same for rbm_b200_block_gibbs_stats: the SMEM variant needs room for bf16 copies of the final
+ * states when the prior has 65 - 256 units per side (its statistics are a tensor-core GEMM over those
+ * tiles); without it the statistics are computed from the fp32 outputs by the GENERAL kernels. */
+RBM_B200_API size_t rbm_b200_block_gibbs_stats_workspace(int32_t n_visible, int32_t n_hidden, int64_t B, int variant);
 /* Number of CUDA kernels one rbm_b200_block_gibbs call with these arguments launches on the current
  * device (the UMMA variant runs all 2k half-steps in ONE dataflow kernel when a half-step has few
  * tiles per SM, else one kernel per half-step).  Host only; -1 without a device. */

@@ -106,3 +106,31 @@ def test_negative_phase_statistics_fused_into_the_final_sweep(nV, nH, B, k):
     e, (S3, sv3, sh3) = s3.negative_phase()
     np.testing.assert_allclose(S3.cpu().numpy(), vn.T @ hn / B, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(e.item(), orc.energy_exp(v.cpu().numpy(), h.cpu().numpy(), W, a, c), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("nV,nH,B,k", [(256, 256, 1024, 20), (200, 200, 500, 2), (130, 70, 301, 1), (65, 256, 4099, 1),
+                                       (128, 128, 20000, 2)])
+def test_smem_statistics_from_the_final_sweep_tiles(nV, nH, B, k):
+    """Priors of 65 - 256 units on the SMEM variant (BASELINE configs[2]: 256 x 256, 1024 chains x 20 steps): the final
+    sweep leaves bf16 {0,1} tiles of (v, h) in the workspace and <vh>, <v>, <h> are a tcgen05 GEMM + column sums over
+    them - no fp32 SIMT pass over the fp32 outputs.  Raw counts are integers: they equal the statistics of the returned
+    states EXACTLY (autograd of GumBolt.energy_exp, gumbolt.py:109-134)."""
+    import divae_b200
+    from test_gpu_umma import make_rbm, rand_params
+    W, a, c = rand_params(nV, nH, 0.1, 7 * nV + nH)
+    rbm = make_rbm(W, a, c)
+    s = divae_b200.PCD(batch_size=B, RBM=rbm, n_gibbs_sampling_steps=k, seed=31, variant="smem")
+    v, h, (S, sv, sh), e = s.block_gibbs_sampling(_stats_scale=1.0)
+    vt, ht = v.double(), h.double()
+    assert torch.equal(S.double(), vt.t() @ ht)
+    assert torch.equal(sv.double(), vt.sum(0)) and torch.equal(sh.double(), ht.sum(0))
+    # the samples are those of the plain call
+    s2 = divae_b200.PCD(batch_size=B, RBM=rbm, n_gibbs_sampling_steps=k, seed=31, variant="smem")
+    v2, h2 = s2.block_gibbs_sampling()
+    assert torch.equal(v, v2) and torch.equal(h, h2)
+    e3, (S3, sv3, sh3) = divae_b200.PCD(batch_size=B, RBM=rbm, n_gibbs_sampling_steps=k, seed=31, variant="smem").negative_phase()
+    torch.testing.assert_close(S3.double(), vt.t() @ ht / B, rtol=1e-6, atol=1e-7)
+    Wd = torch.from_numpy(W).double().to(vt.device)
+    ref = -(((vt @ Wd) * ht).sum(1) + vt @ torch.from_numpy(a).double().to(vt.device)
+            + ht @ torch.from_numpy(c).double().to(vt.device)).mean()
+    assert abs(e3.item() - ref.item()) <= 1e-4 * max(1.0, abs(ref.item()))
