@@ -81,6 +81,10 @@ PROTOTYPES = {
     "rbm_b200_ais_run_ex": (_int, [_P, _i64, ctypes.POINTER(ctypes.c_double), _i32, _u64, _u64, _vp, _int, _vp, _sz, _vp]),
     "rbm_b200_decoder_workspace": (_sz, [_D, _i64]),
     "rbm_b200_decoder_forward": (_int, [_D, _vp, _i64, _vp, _vp, _vp, _u64, _u64, _u64, _int, _vp, _sz, _vp]),
+    "rbm_b200_gemm_workspace": (_sz, [_i64, _i32, _i32]),
+    "rbm_b200_gemm": (_int, [_int, _i64, _i32, _i32, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
+    "rbm_b200_gemm_tn_workspace": (_sz, [_i64, _i32, _i32]),
+    "rbm_b200_gemm_tn": (_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "rbm_b200_gumbel_smooth": (_int, [_vp, _vp, _i64, _i32, _f32, _int, _int, _u64, _u64, _u64, ctypes.c_uint32, _vp]),
 }
 

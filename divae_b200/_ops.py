@@ -111,11 +111,126 @@ def half_step(rbm_pack, direction, x, mode, uniforms=None, seed=0, chain_offset=
     return out.squeeze(0) if squeeze else out
 
 
+_gemm_ws = {}   # (device index, stream) -> grow-only uint8 workspace shared by the GEMM wrappers below
+
+
+def _workspace(dev, nbytes):
+    key = (dev.index, _stream().value)
+    ws = _gemm_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _gemm_ws[key] = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
+    return ws
+
+
+def gemm(a, b, trans_b, bias=None, relu=False):
+    """act(a @ b.T + bias) (trans_b=True, b is [N, K]) or act(a @ b + bias) (trans_b=False, b is [K, N]) for fp32
+    row-major operands: ONE tcgen05 GEMM on bf16 high + low splits of both operands (rbm_b200_gemm; ~2^-16 relative)."""
+    lib = _lib.load()
+    a = _f32c(a, "gemm operand"); b = _f32c(b, "gemm operand")
+    if a.dim() != 2 or b.dim() != 2:
+        raise RuntimeError("gemm needs 2-D operands, got %s and %s" % (tuple(a.shape), tuple(b.shape)))
+    M, K = a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    if (b.shape[1] if trans_b else b.shape[0]) != K:
+        raise RuntimeError("size mismatch: gemm got %s and %s (trans_b=%s)" % (tuple(a.shape), tuple(b.shape), trans_b))
+    if bias is not None:
+        bias = _f32c(bias, "gemm bias")
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if M == 0:
+        return out
+    nbytes = lib.rbm_b200_gemm_workspace(M, N, K)
+    ws = _workspace(a.device, nbytes)
+    with _on_device(a.device):
+        _lib.check(lib.rbm_b200_gemm(1 if trans_b else 0, M, N, K, _ptr(a), _ptr(b), _ptr(bias), 1 if relu else 0, _ptr(out),
+                                     _ptr(ws), ws.numel(), _stream()), "gemm")
+    return out
+
+
+def gemm_tn(a, b):
+    """a.T @ b for fp32 row-major a [R, M], b [R, N] (weight gradients: the reduction runs over the batch): three
+    tcgen05 products of the bf16 high / low splits, split over the rows, partial tiles added in fp32 (rbm_b200_gemm_tn)."""
+    lib = _lib.load()
+    a = _f32c(a, "gemm operand"); b = _f32c(b, "gemm operand")
+    if a.dim() != 2 or b.dim() != 2 or a.shape[0] != b.shape[0]:
+        raise RuntimeError("size mismatch: gemm_tn got %s and %s" % (tuple(a.shape), tuple(b.shape)))
+    R, M = a.shape
+    N = b.shape[1]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    nbytes = lib.rbm_b200_gemm_tn_workspace(R, M, N)
+    ws = _workspace(a.device, nbytes)
+    with _on_device(a.device):
+        _lib.check(lib.rbm_b200_gemm_tn(_ptr(a), _ptr(b), R, M, N, _ptr(out), _ptr(ws), ws.numel(), _stream()), "gemm_tn")
+    return out
+
+
+class _Linear(torch.autograd.Function):
+    """y = act(x W^T + b) (torch.nn.Linear + optional ReLU: the layers of hierarchicalEncoder.py:86-96 and
+    basicCoders.py:28-84) with forward AND backward on the tensor cores:
+    dx = g' W, dW = g'^T x, db = sum_rows g' with g' = g * [y > 0] behind a ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        y = gemm(x, W, True, bias=b, relu=relu)
+        ctx.save_for_backward(x, W, y if relu else None)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W, y = ctx.saved_tensors
+        g = g.contiguous()
+        if y is not None:
+            g = g * (y > 0)
+        dx = gemm(g, W, False) if ctx.needs_input_grad[0] else None
+        dW = gemm_tn(g, x) if ctx.needs_input_grad[1] else None
+        db = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dW, db, None
+
+
+def linear(x, W, b=None, relu=False):
+    return _Linear.apply(x, W, b, relu)
+
+
+class _GumbelSmooth(torch.autograd.Function):
+    """(clamp(l, -88, 88), GumbelMod(clamp(l), beta, is_training)) with Philox draws (hierarchicalEncoder.py:167-176,
+    gumbelmod.py:14-24).  Backward: d l = (g_logits + g_samples * beta * z (1 - z)) * [-88 <= l <= 88] in training mode;
+    the evaluation-mode gate has no gradient (heaviside)."""
+
+    @staticmethod
+    def forward(ctx, raw, beta, is_training, seed, chain_offset, step, unit_offset):
+        lib = _lib.load()
+        raw = _f32c(raw, "logits")
+        logits = raw.clone()
+        samples = torch.empty_like(logits)
+        with _on_device(raw.device):
+            _lib.check(lib.rbm_b200_gumbel_smooth(_ptr(logits), _ptr(samples), logits.shape[0], logits.shape[1], float(beta),
+                                                  1 if is_training else 0, 1, int(seed), int(chain_offset), int(step),
+                                                  int(unit_offset), _stream()), "gumbel_smooth")
+        ctx.save_for_backward(raw, samples)
+        ctx.beta, ctx.is_training = float(beta), bool(is_training)
+        if not is_training:
+            ctx.mark_non_differentiable(samples)
+        return logits, samples
+
+    @staticmethod
+    def backward(ctx, g_logits, g_samples):
+        raw, z = ctx.saved_tensors
+        g = g_logits
+        if ctx.is_training:
+            g = g + g_samples * (ctx.beta * z * (1.0 - z))
+        return g * ((raw >= -88.0) & (raw <= 88.0)), None, None, None, None, None, None
+
+
+def gumbel_smooth(raw_logits, beta, is_training, seed=0, chain_offset=0, step=0, unit_offset=0):
+    return _GumbelSmooth.apply(raw_logits, beta, is_training, seed, chain_offset, step, unit_offset)
+
+
 class _MeanFieldHalfStep(torch.autograd.Function):
     """sigmoid(x W + c) / sigmoid(x W^T + a) with the forward in CUDA (gibbsSampler.py:20-28).
 
     Backward is the analytic gradient of the same expression (the reference gets it
-    from autograd): g_pre = g * p (1 - p); dx = g_pre Wop^T; dW, dbias accordingly.
+    from autograd): g_pre = g * p (1 - p); dx = g_pre Wop^T; dW, dbias accordingly - the products through
+    rbm_b200_gemm / rbm_b200_gemm_tn (tensor cores), not ATen matmuls.
     """
 
     @staticmethod
@@ -130,12 +245,13 @@ class _MeanFieldHalfStep(torch.autograd.Function):
         x, W, p = ctx.saved_tensors
         gp = g * p * (1.0 - p)
         x2, gp2 = (x.unsqueeze(0), gp.unsqueeze(0)) if x.dim() == 1 else (x, gp)
-        if ctx.direction == 0:
-            dx = gp2 @ W.t()
-            dW = x2.t() @ gp2
-        else:
-            dx = gp2 @ W
-            dW = gp2.t() @ x2
+        gp2 = gp2.contiguous()
+        if ctx.direction == 0:          # p = sigmoid(x W + c): dx = g' W^T, dW = x^T g'   (tcgen05 GEMMs, split bf16)
+            dx = gemm(gp2, W, True)
+            dW = gemm_tn(x2, gp2)
+        else:                           # p = sigmoid(x W^T + a): dx = g' W, dW = g'^T x
+            dx = gemm(gp2, W, False)
+            dW = gemm_tn(gp2, x2)
         dbias = gp2.sum(0)
         if x.dim() == 1:
             dx = dx.squeeze(0)
@@ -172,9 +288,10 @@ class _Energy(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         v, h, W, a, c = ctx.saved_tensors
-        gv = -(g[:, None] * (a[None, :] + h @ W.t()))
-        gh = -(g[:, None] * (c[None, :] + v @ W))
-        gW = -(v * g[:, None]).t() @ h
+        # three tcgen05 GEMMs on split-bf16 operands (rbm_b200_gemm / rbm_b200_gemm_tn) instead of ATen matmuls
+        gv = -(g[:, None] * gemm(h, W, True, bias=a)) if ctx.needs_input_grad[0] else None     # a + h W^T
+        gh = -(g[:, None] * gemm(v, W, False, bias=c)) if ctx.needs_input_grad[1] else None    # c + v W
+        gW = -gemm_tn(v * g[:, None], h) if ctx.needs_input_grad[2] else None
         ga = -(v * g[:, None]).sum(0)
         gc = -(h * g[:, None]).sum(0)
         return gv, gh, gW, ga, gc, None
@@ -233,6 +350,6 @@ def energy_exp(rbm, rbm_vis, rbm_hid):
 
     Same value and the same gradients w.r.t. the (real-valued, smoothed) samples and (W, a, c) as the
     reference expression, without materialising W broadcast to [B, nV, nH]: forward is the fused energy
-    kernel (rbm_b200_energy), backward three [B,n] x [n,n] products."""
+    kernel (rbm_b200_energy), backward three [B,n] x [n,n] products on the tensor cores (split-bf16 tcgen05 GEMMs)."""
     pack = rbm._pack.pack(rbm, need_bf16=False)
     return energy(rbm, pack, rbm_vis, rbm_hid).mean()

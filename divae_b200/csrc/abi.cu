@@ -407,4 +407,34 @@ int rbm_b200_gumbel_smooth(float* logits, float* samples, int64_t B, int32_t n, 
                        (cudaStream_t)stream);
 }
 
+size_t rbm_b200_gemm_workspace(int64_t M, int32_t N, int32_t K) {
+  if (M < 0 || N <= 0 || K <= 0) return 0;
+  return umma_gemm_workspace_bytes(M, N, K);
+}
+
+int rbm_b200_gemm(int trans_b, int64_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias, int relu,
+                  float* C, void* workspace, size_t workspace_bytes, void* stream) {
+  RBM_REQUIRE(M >= 0 && N >= 1 && K >= 1 && N <= 16384 && K <= 16384, RBM_B200_ERR_INVALID,
+              "gemm shape out of range: M %lld, N %d, K %d", (long long)M, N, K);
+  RBM_REQUIRE(M == 0 || (A && B && C), RBM_B200_ERR_INVALID, "NULL pointer");
+  int rc = require_device();
+  if (rc) return rc;
+  return umma_gemm(trans_b ? 1 : 0, M, N, K, A, B, bias, relu, C, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t rbm_b200_gemm_tn_workspace(int64_t kdim, int32_t M, int32_t N) {
+  if (kdim < 0 || M <= 0 || N <= 0) return 0;
+  return umma_gemm_tn_workspace_bytes(kdim, M, N);
+}
+
+int rbm_b200_gemm_tn(const float* A, const float* B, int64_t kdim, int32_t M, int32_t N, float* C, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  RBM_REQUIRE(kdim >= 0 && M >= 1 && N >= 1 && M <= 16384 && N <= 16384, RBM_B200_ERR_INVALID,
+              "gemm shape out of range: kdim %lld, M %d, N %d", (long long)kdim, M, N);
+  RBM_REQUIRE(C != nullptr && (kdim == 0 || (A && B)), RBM_B200_ERR_INVALID, "NULL pointer");
+  int rc = require_device();
+  if (rc) return rc;
+  return umma_gemm_tn(A, B, kdim, M, N, C, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -550,28 +550,38 @@ int launch_stats(const CUtensorMap& tv, const CUtensorMap& th, const StatsArgs& 
   return check_launch("umma_stats_kernel");
 }
 
+// C[M, N] += A^T B over `kdim` rows: A is [kdim, >= M] bf16 with row pitch lda (elements), B is [kdim, >= N] bf16 with row
+// pitch ldb; both operands are read MN-major straight from row-major storage ([64 rows x 64 columns] TMA boxes), split-K
+// over CTAs, fp32 partial tiles ADDED with red.global.  C has row pitch N.
+int launch_tn_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t kdim, int M, int N, float* C, int sm_count,
+                   cudaStream_t st) {
+  int rc;
+  CUtensorMap tv, th;
+  // kdim rows: rows beyond the end read as zeros
+  if ((rc = make_tmap(&tv, A, (uint64_t)kdim, (uint64_t)round_up(M, 64), (uint64_t)lda, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&th, B, (uint64_t)kdim, (uint64_t)round_up(N, 64), (uint64_t)ldb, BLOCK_K))) return rc;
+  const int Np = round_up(N, 64);
+  const int bn = round_up(Np, 128) < round_up(Np, 256) ? 128 : 256;
+  StatsArgs a{};
+  a.S_vh = C; a.nV = M; a.nH = N;
+  const int tiles_m = ceil_div(M, BLOCK_M);
+  a.tiles_n = ceil_div(N, bn);
+  a.tiles = tiles_m * a.tiles_n;
+  a.k_blocks = (int)ceil_div64(kdim, BLOCK_K);
+  // split the rows so that one wave of CTAs covers the GPU; every split owns at least one K block
+  int splits = std::max(1, std::min(a.k_blocks, sm_count / a.tiles));
+  a.kb_per_split = ceil_div(a.k_blocks, splits);
+  splits = ceil_div(a.k_blocks, a.kb_per_split);
+  return bn == 256 ? launch_stats<256>(tv, th, a, a.tiles * splits, st) : launch_stats<128>(tv, th, a, a.tiles * splits, st);
+}
+
 // Raw counts of the final (v, h) pair of this call's chains, ADDED to S_vh [nV, nH], S_v [nV], S_h [nH].
 int umma_stats(const Plan& pl, const __nv_bfloat16* Vs, const __nv_bfloat16* Hs, int64_t B, float* S_vh, float* S_v,
                float* S_h, int sm_count, cudaStream_t st) {
   RBM_REQUIRE(B <= (int64_t)1 << 24, RBM_B200_ERR_INVALID,
               "fused statistics count in fp32: at most 2^24 chains per call (got %lld)", (long long)B);
-  int rc;
-  CUtensorMap tv, th;
   // B rows: the padding chains read as zeros
-  if ((rc = make_tmap(&tv, Vs, (uint64_t)B, (uint64_t)pl.nVp, (uint64_t)pl.nVp, BLOCK_K))) return rc;
-  if ((rc = make_tmap(&th, Hs, (uint64_t)B, (uint64_t)pl.nHp, (uint64_t)pl.nHp, BLOCK_K))) return rc;
-  const int bn = round_up(pl.nHp, 128) < round_up(pl.nHp, 256) ? 128 : 256;
-  StatsArgs a{};
-  a.S_vh = S_vh; a.nV = pl.nV; a.nH = pl.nH;
-  const int tiles_m = ceil_div(pl.nV, BLOCK_M);
-  a.tiles_n = ceil_div(pl.nH, bn);
-  a.tiles = tiles_m * a.tiles_n;
-  a.k_blocks = (int)ceil_div64(B, BLOCK_K);
-  // split the chains so that one wave of CTAs covers the GPU; every split owns at least one K block
-  int splits = std::max(1, std::min(a.k_blocks, sm_count / a.tiles));
-  a.kb_per_split = ceil_div(a.k_blocks, splits);
-  splits = ceil_div(a.k_blocks, a.kb_per_split);
-  rc = bn == 256 ? launch_stats<256>(tv, th, a, a.tiles * splits, st) : launch_stats<128>(tv, th, a, a.tiles * splits, st);
+  int rc = launch_tn_gemm(Vs, pl.nVp, Hs, pl.nHp, B, pl.nV, pl.nH, S_vh, sm_count, st);
   if (rc) return rc;
   const int64_t rows_per_block = std::max<int64_t>(64, ceil_div64(B, 4 * sm_count));
   const unsigned row_blocks = (unsigned)ceil_div64(B, rows_per_block);
@@ -580,6 +590,27 @@ int umma_stats(const Plan& pl, const __nv_bfloat16* Vs, const __nv_bfloat16* Hs,
   return check_launch("colsum_bf16_kernel");
 }
 
+// x [rows, n] fp32 -> [rows, 2 np] bf16 = [x_hi | x_lo] (x = x_hi + x_lo to ~2^-17), columns zero padded to np
+__global__ void split_rows_kernel(const float* __restrict__ x, int64_t rows, int n, uint16_t* __restrict__ dst, int np) {
+  const int groups = np >> 3;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * groups) return;
+  const int64_t r = idx / groups;
+  const int c0 = (int)(idx % groups) * 8;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float val = c < n ? __ldg(x + r * n + c) : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(val);
+    const __nv_bfloat16 l = __float2bfloat16_rn(val - __bfloat162float(h));
+    if (j & 1) { hi[j >> 1] |= (uint32_t)__bfloat16_as_ushort(h) << 16; lo[j >> 1] |= (uint32_t)__bfloat16_as_ushort(l) << 16; }
+    else { hi[j >> 1] = __bfloat16_as_ushort(h); lo[j >> 1] = __bfloat16_as_ushort(l); }
+  }
+  uint16_t* row = dst + r * (2 * (int64_t)np);
+  *reinterpret_cast<uint4*>(row + c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(row + np + c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
 
 }  // namespace
 
@@ -590,6 +621,35 @@ extern "C" __attribute__((visibility("default"))) int rbm_b200_debug_resident_tr
 }
 namespace rbm {
 #endif
+
+// C[M, N] = A^T B for fp32 A [kdim, M], B [kdim, N] (the weight gradient dW = dY^T X of a linear layer, the <v h^T>
+// gradient of the energy): operands split into bf16 high + low parts, three tensor-core products
+// (hi hi + hi lo + lo hi, ~2^-16 relative), partial tiles of the K splits added in fp32.
+size_t umma_gemm_tn_workspace_bytes(int64_t kdim, int M, int N) {
+  return (size_t)kdim * 2 * (size_t)(round_up(M, 64) + round_up(N, 64)) * 2 + 2048;
+}
+
+int umma_gemm_tn(const float* A, const float* B, int64_t kdim, int M, int N, float* C, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+  RBM_REQUIRE(ws != nullptr && ws_bytes >= umma_gemm_tn_workspace_bytes(kdim, M, N), RBM_B200_ERR_WORKSPACE,
+              "gemm (A^T B) needs %zu bytes of workspace, got %zu", umma_gemm_tn_workspace_bytes(kdim, M, N), ws_bytes);
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  RBM_REQUIRE(di.cc_major == 10, RBM_B200_ERR_NO_DEVICE, "the tensor-core GEMM needs an sm_100 device (got cc %d.x)", di.cc_major);
+  RBM_CUDA_TRY(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+  if (kdim == 0) return 0;
+  const int Mp = round_up(M, 64), Np = round_up(N, 64);
+  uint16_t* At = reinterpret_cast<uint16_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  uint16_t* Bt = At + (size_t)kdim * 2 * Mp;
+  split_rows_kernel<<<(unsigned)ceil_div64(kdim * (Mp / 8), 256), 256, 0, st>>>(A, kdim, M, At, Mp);
+  split_rows_kernel<<<(unsigned)ceil_div64(kdim * (Np / 8), 256), 256, 0, st>>>(B, kdim, N, Bt, Np);
+  if ((rc = check_launch("split_rows_kernel"))) return rc;
+  // (hi, hi), (hi, lo), (lo, hi)
+  if ((rc = launch_tn_gemm(At, 2 * Mp, Bt, 2 * Np, kdim, M, N, C, di.sm_count, st))) return rc;
+  if ((rc = launch_tn_gemm(At, 2 * Mp, Bt + Np, 2 * Np, kdim, M, N, C, di.sm_count, st))) return rc;
+  return launch_tn_gemm(At + Mp, 2 * Mp, Bt, 2 * Np, kdim, M, N, C, di.sm_count, st);
+}
 
 bool umma_variant_supported(int nV, int nH) { return nV >= 1 && nH >= 1 && nV <= 16384 && nH <= 16384; }
 

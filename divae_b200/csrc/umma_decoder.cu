@@ -97,6 +97,39 @@ __global__ void gumbel_smooth_kernel(float* __restrict__ logits, float* __restri
   }
 }
 
+// B [K, N] fp32 (row-major, N contiguous) -> [3 Kp, Np] bf16 = [B_hi ; B_lo ; B_hi] stacked along K, zero padded: the
+// MN-major B operand of C = A B with split operands (the K blocks of [A_hi | A_hi | A_lo] meet them in this order)
+__global__ void split_weight_rows_kernel(const float* __restrict__ Bm, int K, int N, uint16_t* __restrict__ dst, int Kp, int Np) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Kp * Np) return;
+  const int r = (int)(idx / Np), c = (int)(idx % Np);
+  const float val = (r < K && c < N) ? Bm[(int64_t)r * N + c] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
+  dst[(int64_t)r * Np + c] = __bfloat16_as_ushort(hi);
+  dst[((int64_t)Kp + r) * Np + c] = __bfloat16_as_ushort(lo);
+  dst[((int64_t)2 * Kp + r) * Np + c] = __bfloat16_as_ushort(hi);
+}
+
+struct GemmPlan {
+  int64_t rows_pad;
+  int Kp, Np, bn;
+  size_t off_A, off_B, off_bias, total;
+};
+GemmPlan make_gemm_plan(int64_t M, int N, int K) {
+  GemmPlan g;
+  g.rows_pad = ceil_div64(std::max<int64_t>(M, 1), 2 * BLOCK_M) * (2 * BLOCK_M);
+  g.Kp = round_up(K, 64); g.Np = round_up(N, 64);
+  g.bn = pick_block_n(g.Np, g.rows_pad);
+  auto align = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  size_t o = 0;
+  g.off_A = o; o = align(o + (size_t)g.rows_pad * 2 * g.Kp * 2);
+  g.off_B = o; o = align(o + (size_t)round_up(g.Np, 256) * 3 * g.Kp * 2);
+  g.off_bias = o; o = align(o + (size_t)round_up(g.Np, 256) * 4);
+  g.total = o + 1024;
+  return g;
+}
+
 struct LayerPlan {
   const rbm_b200_linear* lin;
   int Kp, Np, bn;
@@ -161,6 +194,13 @@ int make_decoder_plan(const rbm_b200_decoder* d, int64_t B, DecoderPlan* out) {
   return 0;
 }
 
+// B operand MN-major ([K, N] row-major storage): C = A B
+int launch_linear_nn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HalfStepArgs& a,
+                     int sm_count, cudaStream_t st) {
+  return bn == 256 ? launch_half_step_impl<256, true, EPI_LINEAR_F32, 1, true>(ta, tb, to, a, sm_count, st)
+                   : launch_half_step_impl<128, true, EPI_LINEAR_F32, 1, true>(ta, tb, to, a, sm_count, st);
+}
+
 template <int EPI>
 int launch_linear(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const HalfStepArgs& a,
                   int sm_count, cudaStream_t st) {
@@ -177,6 +217,52 @@ int gumbel_smooth(float* logits, float* samples, int64_t B, int n, float beta, i
                                                                         make_draw_ctx(seed, step, TAG_SMOOTH), chain_offset,
                                                                         unit_offset);
   return check_launch("gumbel_smooth_kernel");
+}
+
+// C [M, N] = act(A op(B) + bias) for fp32 A [M, K]: op(B) = B^T with B [N, K] (trans_b = 1: y = x W^T, an nn.Linear) or
+// op(B) = B with B [K, N] (trans_b = 0: dx = dy W).  One launch of the tcgen05 kernel of a Gibbs half-step over the
+// tripled K axis of the split operands; bias may be NULL.
+size_t umma_gemm_workspace_bytes(int64_t M, int N, int K) { return make_gemm_plan(M, N, K).total; }
+
+int umma_gemm(int trans_b, int64_t M, int N, int K, const float* A, const float* Bm, const float* bias, int relu, float* C,
+              void* ws, size_t ws_bytes, cudaStream_t st) {
+  const GemmPlan g = make_gemm_plan(M, N, K);
+  RBM_REQUIRE(ws != nullptr && ws_bytes >= g.total, RBM_B200_ERR_WORKSPACE, "gemm needs %zu bytes of workspace, got %zu", g.total, ws_bytes);
+  if (M == 0) return 0;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  RBM_REQUIRE(di.cc_major == 10, RBM_B200_ERR_NO_DEVICE, "the tensor-core GEMM needs an sm_100 device (got cc %d.x)", di.cc_major);
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  uint16_t* As = reinterpret_cast<uint16_t*>(base + g.off_A);
+  uint16_t* Bs = reinterpret_cast<uint16_t*>(base + g.off_B);
+  float* bias_p = reinterpret_cast<float*>(base + g.off_bias);
+  split_input_kernel<<<(unsigned)ceil_div64(g.rows_pad * (g.Kp / 8), 256), 256, 0, st>>>(A, M, K, As, g.rows_pad, g.Kp);
+  const int64_t nb = (int64_t)g.Np * g.Kp;
+  if (trans_b) split_weight_kernel<<<(unsigned)ceil_div64(nb, 256), 256, 0, st>>>(Bm, N, K, Bs, g.Np, g.Kp);
+  else split_weight_rows_kernel<<<(unsigned)ceil_div64(nb, 256), 256, 0, st>>>(Bm, K, N, Bs, g.Kp, g.Np);
+  const int np256 = round_up(g.Np, 256);
+  if (bias != nullptr) pad_bias_kernel<<<ceil_div(np256, 256), 256, 0, st>>>(bias, bias_p, N, np256, 1.f);
+  else RBM_CUDA_TRY(cudaMemsetAsync(bias_p, 0, sizeof(float) * (size_t)np256, st));
+  if ((rc = check_launch("gemm staging kernels"))) return rc;
+  CUtensorMap ta, tb, to;
+  if ((rc = make_tmap(&ta, As, (uint64_t)g.rows_pad, (uint64_t)(2 * g.Kp), (uint64_t)(2 * g.Kp), BLOCK_M))) return rc;
+  if (trans_b) rc = make_tmap(&tb, Bs, (uint64_t)g.Np, (uint64_t)(3 * g.Kp), (uint64_t)(3 * g.Kp), (uint32_t)g.bn);
+  else rc = make_tmap(&tb, Bs, (uint64_t)(3 * g.Kp), (uint64_t)g.Np, (uint64_t)g.Np, BLOCK_K);
+  if (rc) return rc;
+  HalfStepArgs a{};
+  a.nbias = bias_p;
+  a.ldo = g.Np; a.m_tiles = (int)(g.rows_pad / BLOCK_M); a.n_tiles = ceil_div(g.Np, g.bn);
+  a.k_blocks = 3 * g.Kp / BLOCK_K; a.n_valid = N; a.rows_valid = M;
+  a.out_f32 = C; a.ld_out = N; a.relu = relu ? 1 : 0;
+  a.f32_tma = (N % 4 == 0 && ((uintptr_t)C & 15) == 0) ? 1 : 0;
+  if (a.f32_tma) {
+    if ((rc = make_tmap_f32(&to, C, (uint64_t)M, (uint64_t)N, (uint64_t)N, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  } else {
+    to = ta;
+  }
+  return trans_b ? launch_linear<EPI_LINEAR_F32>(g.bn, ta, tb, to, a, di.sm_count, st)
+                 : launch_linear_nn(g.bn, ta, tb, to, a, di.sm_count, st);
 }
 
 size_t umma_decoder_workspace_bytes(const rbm_b200_decoder* d, int64_t B) {

@@ -61,6 +61,15 @@ int umma_decoder_forward(const rbm_b200_decoder* d, const float* x, int64_t B, f
                          float* samples, uint64_t seed, uint64_t chain_offset, uint64_t step, int params_staged,
                          void* ws, size_t ws_bytes, cudaStream_t st);
 
+// fp32-grade GEMMs on the tensor cores (split bf16 operands) for the backward passes of the rows next to the path:
+//   umma_gemm     C [M,N] = act(A [M,K] op(B) + bias), op(B) = B^T for B [N,K] (trans_b = 1) or B for B [K,N] (trans_b = 0)
+//   umma_gemm_tn  C [M,N] = A^T B for A [kdim,M], B [kdim,N]
+size_t umma_gemm_workspace_bytes(int64_t M, int N, int K);
+int umma_gemm(int trans_b, int64_t M, int N, int K, const float* A, const float* B, const float* bias, int relu, float* C,
+              void* ws, size_t ws_bytes, cudaStream_t st);
+size_t umma_gemm_tn_workspace_bytes(int64_t kdim, int M, int N);
+int umma_gemm_tn(const float* A, const float* B, int64_t kdim, int M, int N, float* C, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // posterior side: clamp + Gumbel smoothing / gate of encoder logits, Philox draws
 int gumbel_smooth(float* logits, float* samples, int64_t B, int n, float beta, int is_training, int clamp, uint64_t seed,
                   uint64_t chain_offset, uint64_t step, uint32_t unit_offset, cudaStream_t st);

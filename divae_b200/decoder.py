@@ -144,7 +144,10 @@ class EncoderRunner:
     Per hierarchy level: logits = clamp(net(cat([x] + samples)), -88, 88) - the level's MLP through
     rbm_b200_decoder_forward (tcgen05 GEMMs on split-bf16 operands) - and
     samples = GumbelMod(logits, beta, is_training) through rbm_b200_gumbel_smooth (Philox draws).
-    Forward only: there is no backward pass, so training keeps the reference's torch encoder."""
+    With autograd enabled (training) the same forward runs through autograd Functions whose backward passes are
+    tcgen05 GEMMs as well (`_ops.linear`: dx = g W, dW = g^T x on split-bf16 operands; `_ops.gumbel_smooth`:
+    beta z (1 - z) and the clamp mask), so the posterior side of a training step stays on the B200 path; under
+    torch.no_grad() the staged one-launch-per-layer inference path is used."""
 
     def __init__(self, encoder, beta=None):
         nets = getattr(encoder, "_networks", None)
@@ -154,6 +157,7 @@ class EncoderRunner:
         if smoother is not None and type(smoother).__name__ != "GumbelMod":
             raise RuntimeError("divae_b200 encoder: only the Gumbel smoother (gumbelmod.py) is implemented, got %r" % (smoother,))
         self._levels = []
+        self._linears = []
         for net in nets:
             mods = list(net)
             linears = [m for m in mods if isinstance(m, torch.nn.Linear)]
@@ -161,6 +165,7 @@ class EncoderRunner:
             if not linears or any(not isinstance(m, (torch.nn.ReLU, torch.nn.Identity)) for m in others):
                 raise RuntimeError("divae_b200 encoder: levels must be Linear/ReLU stacks (hierarchicalEncoder.py:86-96)")
             self._levels.append(DecoderRunner(_Chain(linears)))
+            self._linears.append(linears)
         if beta is None:
             cfg = getattr(encoder, "_config", None)
             beta = getattr(getattr(cfg, "model", None), "beta_smoothing_fct", None)
@@ -178,6 +183,17 @@ class EncoderRunner:
         x = _ops._f32c(x, "encoder input")
         B = x.shape[0]
         post_logits, post_samples = [], []
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for ls in self._linears for m in ls for p in m.parameters())):
+            # training: differentiable forward, every product (forward and backward) a tcgen05 GEMM
+            for lvl, linears in enumerate(self._linears):
+                cur = torch.cat([x] + post_samples, dim=1) if post_samples else x
+                for i, m in enumerate(linears):
+                    cur = _ops.linear(cur, m.weight, m.bias, relu=(i + 1 < len(linears)))
+                logits, samples = _ops.gumbel_smooth(cur, self.beta, is_training, seed, chain_offset, step, lvl * self.n_latent)
+                if scale is not None:
+                    samples = samples * _ops._f32c(scale, "scale").reshape(B, 1)
+                post_logits.append(logits); post_samples.append(samples)
+            return torch.tensor(self.beta, dtype=torch.float, device=x.device), post_logits, post_samples
         with torch.no_grad(), _ops._on_device(x.device):
             for lvl, runner in enumerate(self._levels):
                 inp = torch.cat([x] + post_samples, dim=1) if post_samples else x

@@ -292,6 +292,27 @@ RBM_B200_API int rbm_b200_gumbel_smooth(float *logits, float *samples, int64_t B
                                         int is_training, int clamp, uint64_t seed, uint64_t chain_offset,
                                         uint64_t step, uint32_t unit_offset, void *stream);
 
+/* ---- backward passes of the rows next to the path --------------
+ * The reference gets these gradients from torch autograd, i.e. from ATen matmuls:
+ *   energy_exp on posterior samples          models/autoencoders/gumbolt.py:97-99,118-132
+ *   mean-field half-steps                    models/samplers/gibbsSampler.py:20-28
+ *   nn.Linear layers of the encoder/decoder  models/networks/hierarchicalEncoder.py:139-183, basicCoders.py:28-84
+ * Here every product is a tcgen05 GEMM with fp32-grade accuracy: both operands are split into bf16 high + low
+ * parts and three partial products (hi hi + hi lo + lo hi, ~2^-16 relative) accumulate in fp32 in TMEM.
+ *
+ * rbm_b200_gemm:    C [M,N] = act(A [M,K] . op(B) + bias)
+ *   trans_b = 1: op(B) = B^T, B is [N,K] row-major (y = x W^T + b: an nn.Linear forward; dv = dE h W^T)
+ *   trans_b = 0: op(B) = B,   B is [K,N] row-major (dx = dy W; dh = dE v W)
+ *   bias [N] or NULL; relu != 0 applies max(0, .).  A, B, C fp32 row-major without padding.
+ * rbm_b200_gemm_tn: C [M,N] = A^T B with A [kdim,M], B [kdim,N] row-major (dW = dy^T x; dW = -(v g)^T h);
+ *   the K splits add their partial tiles with fp32 atomics: the summation order is not fixed. */
+RBM_B200_API size_t rbm_b200_gemm_workspace(int64_t M, int32_t N, int32_t K);
+RBM_B200_API int rbm_b200_gemm(int trans_b, int64_t M, int32_t N, int32_t K, const float *A, const float *B,
+                  const float *bias, int relu, float *C, void *workspace, size_t workspace_bytes, void *stream);
+RBM_B200_API size_t rbm_b200_gemm_tn_workspace(int64_t kdim, int32_t M, int32_t N);
+RBM_B200_API int rbm_b200_gemm_tn(const float *A, const float *B, int64_t kdim, int32_t M, int32_t N, float *C,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
