@@ -22,9 +22,12 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not rh.reference_available(), 
 DEV = torch.device("cuda:0")
 
 
-def _fit(arm, n_batches, seed):
+def _fit(arm, n_batches, seed, accelerate=False):
     ns = rh.load_arm(arm)
     model, cfg = rh.build_gumbolt(ns, DEV, n_latent_nodes=64, seed=seed)
+    if accelerate:
+        from divae_b200 import dropin
+        dropin.accelerate(model, seed=5)
     data = rh.SyntheticData(n_batches, 100, seed=7)
     eng = rh.build_engine(ns, model, cfg, data, DEV)
     # fit() only logs every 100th batch: record every iteration's loss dictionary through the model's loss()
@@ -49,6 +52,8 @@ def fits():
         out[arm] = _fit(arm, 60, seed=0)
     # a second reference run with another torch seed: the run-to-run spread of the reference itself
     out["reference_seed1"] = _fit("reference", 60, seed=1)
+    # encoder forward/backward and energy terms on the tcgen05 GEMMs too (dropin.accelerate)
+    out["accelerated"] = _fit("dropin", 60, seed=0, accelerate=True)
     return out
 
 
@@ -79,6 +84,23 @@ def test_dropin_training_is_statistically_the_reference_training(fits):
         c = np.mean([d[key] for d in ref1[-20:]])
         sd = np.std([d[key] for d in ref[-20:]]) + np.std([d[key] for d in ours[-20:]])
         # within the reference's own seed-to-seed spread (x3) or 3 sigma of the iteration noise, plus a relative slack
+        tol = 3.0 * abs(a - c) + 3.0 * sd / np.sqrt(20) + slack * abs(a)
+        assert abs(a - b) <= tol, (key, a, b, c, tol)
+
+
+def test_accelerated_training_is_statistically_the_reference_training(fits):
+    """dropin.accelerate(): the reference GumBolt trains with its encoder (Linear layers + Gumbel smoother, forward and
+    backward) and both energy terms on the tensor-core GEMMs; loss curves agree with the all-reference run."""
+    ns, model, losses, final = fits["accelerated"]
+    assert hasattr(model, "_b200_encoder_runner") and len(losses) == 60
+    assert all(np.isfinite(list(d.values())).all() for d in losses)
+    assert float(model.encoder._networks[0][0].weight.grad.abs().sum()) > 0     # the encoder was trained through our backward
+    ref, ref1 = fits["reference"][2], fits["reference_seed1"][2]
+    for key, slack in (("loss", 0.03), ("ae_loss", 0.03), ("kl_loss", 0.03), ("neg_energy", 0.2)):
+        a = np.mean([d[key] for d in ref[-20:]])
+        b = np.mean([d[key] for d in losses[-20:]])
+        c = np.mean([d[key] for d in ref1[-20:]])
+        sd = np.std([d[key] for d in ref[-20:]]) + np.std([d[key] for d in losses[-20:]])
         tol = 3.0 * abs(a - c) + 3.0 * sd / np.sqrt(20) + slack * abs(a)
         assert abs(a - b) <= tol, (key, a, b, c, tol)
 
