@@ -353,7 +353,8 @@ ChainCfg pick_chain_cfg(int nVp, int nHp, int64_t rows_pad, int sm_count) {
       if (cols(bn) != best) continue;
       // small priors (K <= 512: a 256-wide tile is only 8 K blocks deep) with few items run better on 128-wide tiles:
       // 512^2 at 5,120 - 8,192 chains 8.1 - 8.8 us per half-step against 12.3 (profiles/r02_chain_sweep_512.txt)
-      if (bn == 256 && std::max(nVp, nHp) <= 512 && items(256) < 2 * (int64_t)sm_count) continue;
+      // (at 16,384 chains, 256 items, the 256-wide pair tiles win again: 18.2 vs 20.1 us for AIS)
+      if (bn == 256 && std::max(nVp, nHp) <= 512 && items(256) < (int64_t)sm_count) continue;
       c.bn = bn;
       if (items(bn) >= (int64_t)sm_count / 2) break;
     }

@@ -147,7 +147,8 @@ class EncoderRunner:
     With autograd enabled (training) the same forward runs through autograd Functions whose backward passes are
     tcgen05 GEMMs as well (`_ops.linear`: dx = g W, dW = g^T x on split-bf16 operands; `_ops.gumbel_smooth`:
     beta z (1 - z) and the clamp mask), so the posterior side of a training step stays on the B200 path; under
-    torch.no_grad() the staged one-launch-per-layer inference path is used."""
+    torch.no_grad(), and in evaluation mode (hard gates carry no gradient), the staged one-launch-per-layer inference
+    path is used."""
 
     def __init__(self, encoder, beta=None):
         nets = getattr(encoder, "_networks", None)
@@ -183,7 +184,8 @@ class EncoderRunner:
         x = _ops._f32c(x, "encoder input")
         B = x.shape[0]
         post_logits, post_samples = [], []
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for ls in self._linears for m in ls for p in m.parameters())):
+        if is_training and torch.is_grad_enabled() and (
+                x.requires_grad or any(p.requires_grad for ls in self._linears for m in ls for p in m.parameters())):
             # training: differentiable forward, every product (forward and backward) a tcgen05 GEMM
             for lvl, linears in enumerate(self._linears):
                 cur = torch.cat([x] + post_samples, dim=1) if post_samples else x

@@ -50,7 +50,7 @@ def load_fixture(g):
 
 
 def close(gpu, ref, tol):
-    err = np.abs(gpu.cpu().numpy().astype(np.float64) - ref) / (1.0 + np.abs(ref))
+    err = np.abs(gpu.detach().cpu().numpy().astype(np.float64) - ref) / (1.0 + np.abs(ref))
     assert err.max() <= tol, err.max()
 
 
@@ -96,6 +96,7 @@ def test_calorimeter_encoder_shape(B):
         close(logits[lvl], pl[lvl], 1e-3)          # level 1 sees level 0's real-valued samples: errors compound
         close(samples[lvl], ps[lvl], 5e-3)
         assert 0.0 <= samples[lvl].min().item() and samples[lvl].max().item() <= 1.0
+        assert samples[lvl].requires_grad        # training mode with trainable parameters: the differentiable path
 
 
 def test_clamp_sharding_and_errors():
