@@ -442,6 +442,7 @@ def run_gibbs(args, ctx):
         return None
     peaks = load_peaks()
     chain_kernel = launches_per_step < 2 * k
+    kernel_name = lib.rbm_b200_kernel_choice(n, n, chains, variant_id).decode()
     flops_per_call = 4.0 * chains * k * n * n
     achieved = flops_per_call / (ms_per_step * 1e-3) / 1e12
     traffic = None
@@ -461,8 +462,7 @@ def run_gibbs(args, ctx):
         "config": {"workload": WORKLOADS["gibbs"][3] if default else "RBM %dx%d, %d chains x %d steps (non-default)" % (n, n, total, k),
                    "n_visible": n, "n_hidden": n, "chains_total": total, "chains_per_gpu": chains, "gibbs_steps": k,
                    "variant": args.variant, "seed": "0x5EED",
-                   "kernel_path": "umma_chain_kernel (all 2k half-steps in one dataflow launch)" if chain_kernel
-                                  else "umma_half_step_kernel (one launch per half-step)",
+                   "kernel_path": kernel_name + (" (all 2k half-steps in one launch)" if chain_kernel else " (one launch per half-step)"),
                    "l2": "between timed calls the fp32 outputs (2 x %d MiB written per call) and the re-initialised state tiles "
                          "(2 x %d MiB bf16) are rewritten%s; no explicit flush"
                          % (chains * n * 4 >> 20, chains * n * 2 >> 20,
@@ -477,7 +477,7 @@ def run_gibbs(args, ctx):
                    "power_w": clocks.get("power_w")},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
-                     "kernel": "umma_chain_kernel" if chain_kernel else "umma_half_step_kernel",
+                     "kernel": kernel_name,
                      "flops_per_launch": flops_per_call if chain_kernel else flops_per_call / (2 * k),
                      "launch_ms": ms_per_step if chain_kernel else ms_per_step / (2 * k),
                      "half_step_us": 1e3 * ms_per_step / (2 * k),
@@ -494,7 +494,7 @@ def run_ais(args, ctx):
     import torch
     import divae_b200
     from divae_b200 import _lib, dist as bdist
-    _lib.load(build_if_missing=False)
+    lib = _lib.load(build_if_missing=False)
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
     n, K = args.n, args.k
     if args.scaling == "strong":
@@ -550,7 +550,8 @@ def run_ais(args, ctx):
         "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                    "reasons": clocks.get("reasons", []), "samples": clocks.get("samples", 0), "power_w": clocks.get("power_w")},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops_sustained"], "traffic": None, "kernel": "umma_chain_kernel (AIS flavour)",
+                     "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                     "kernel": lib.rbm_b200_kernel_choice(n, n, chains, _lib.VARIANTS[args.ais_variant]).decode() + " (AIS flavour)",
                      "flops_per_launch": flops_per_call, "launch_ms": ms_per_step, "half_step_us": 1e3 * ms_per_step / (2 * K - 1),
                      "peak_source": peaks["source"] + " bf16_tflops_sustained (per GPU)",
                      "frac_of_burst": achieved / peaks["tflops_burst"]},

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "rbm_b200_half_step": (_int, [_P, _int, _vp, _vp, _i64, _int, _vp, _u64, _u64, _u64, _vp]),
     "rbm_b200_init_chains": (_int, [_vp, _i64, _i32, _u64, _u64, _u64, _vp]),
     "rbm_b200_block_gibbs_workspace": (_sz, [_i32, _i32, _i64, _int]),
+    "rbm_b200_kernel_choice": (ctypes.c_char_p, [_i32, _i32, _i64, _int]),
     "rbm_b200_block_gibbs_stats_workspace": (_sz, [_i32, _i32, _i64, _int]),
     "rbm_b200_block_gibbs_launch_count": (_i64, [_i32, _i32, _i64, _i32, _int]),
     "rbm_b200_block_gibbs": (_int, [_P, _vp, _vp, _i64, _i32, _int, _u64, _u64, _u64, _int, _vp, _sz, _vp]),

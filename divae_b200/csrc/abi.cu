@@ -156,6 +156,18 @@ size_t rbm_b200_block_gibbs_workspace(int32_t n_visible, int32_t n_hidden, int64
   }
 }
 
+const char* rbm_b200_kernel_choice(int32_t n_visible, int32_t n_hidden, int64_t B, int variant) {
+  if (B <= 0 || n_visible <= 0 || n_hidden <= 0) return "none";
+  if (require_device()) return "unknown (no device)";
+  rbm_b200_params q{};
+  q.n_visible = n_visible; q.n_hidden = n_hidden;
+  switch (pick_variant(&q, B, variant)) {
+    case RBM_B200_VARIANT_UMMA: return umma_kernel_choice(n_visible, n_hidden, B, variant == RBM_B200_VARIANT_UMMA_SPLIT);
+    case RBM_B200_VARIANT_SMEM: return "smem_gibbs_kernel";
+    default: return "general_half_step_kernel";
+  }
+}
+
 size_t rbm_b200_block_gibbs_stats_workspace(int32_t n_visible, int32_t n_hidden, int64_t B, int variant) {
   if (B <= 0 || n_visible <= 0 || n_hidden <= 0) return 0;
   rbm_b200_params q{};

@@ -667,6 +667,16 @@ int umma_stats_tiles(const void* v_tiles, const void* h_tiles, int64_t B, int nV
                     S_vh, S_v, S_h, di.sm_count, st);
 }
 
+// which kernel runs the half-steps of a UMMA-variant call of this shape (reporting / tests)
+const char* umma_kernel_choice(int nV, int nH, int64_t B, bool split_w) {
+  const Plan pl = make_plan(nV, nH, B);
+  DeviceInfo di;
+  if (get_device_info(&di)) return "unknown (no device)";
+  if (resident_enabled(pl.nVp, pl.nHp, pl.rows_pad, split_w, di.sm_count)) return "umma_resident_kernel";
+  if (split_w || chain_enabled(pl.nVp, pl.nHp, pl.rows_pad, di.sm_count)) return "umma_chain_kernel";
+  return "umma_half_step_kernel";
+}
+
 // kernels one umma_block_gibbs call launches (no statistics): 3 parameter staging + 1 initial state + chain + 2 outputs
 int64_t umma_launch_count(int nV, int nH, int64_t B, int k, bool split_w) {
   if (k <= 0) return 5;

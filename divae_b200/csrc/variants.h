@@ -43,6 +43,7 @@ int smem_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, in
 bool umma_variant_supported(int nV, int nH);
 size_t umma_workspace_bytes(int nV, int nH, int64_t B);
 int64_t umma_launch_count(int nV, int nH, int64_t B, int k, bool split_w);
+const char* umma_kernel_choice(int nV, int nH, int64_t B, bool split_w);
 // S_vh/S_v/S_h non-null: raw counts of the final (v, h) are ADDED to them (tensor-core V^T H over the
 // bf16 state tiles, split over the chains); the caller zeroes before and scales after, as for the SMEM variant.
 int umma_block_gibbs(const rbm_b200_params* p, float* v, float* h, int64_t B, int k, int init_chains,

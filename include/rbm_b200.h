@@ -110,6 +110,10 @@ RBM_B200_API int rbm_b200_init_chains(float *v, int64_t B, int32_t n_visible, ui
 /* Bytes of caller-provided workspace rbm_b200_block_gibbs needs for this shape
  * and variant (0 for the GENERAL variant). Host only. */
 RBM_B200_API size_t rbm_b200_block_gibbs_workspace(int32_t n_visible, int32_t n_hidden, int64_t B, int variant);
+/* Name of the kernel that runs the half-steps of a block-Gibbs / AIS call of this shape on the current device
+ * (shape-based choice inside the library: "smem_gibbs_kernel", "umma_resident_kernel", "umma_chain_kernel",
+ * "umma_half_step_kernel", "general_half_step_kernel").  For reports and tests; static string, host only. */
+RBM_B200_API const char *rbm_b200_kernel_choice(int32_t n_visible, int32_t n_hidden, int64_t B, int variant);
 /* Same for rbm_b200_block_gibbs_stats: the SMEM variant needs room for bf16 copies of the final
  * states when the prior has 65 - 256 units per side (its statistics are a tensor-core GEMM over those
  * tiles); without it the statistics are computed from the fp32 outputs by the GENERAL kernels. */

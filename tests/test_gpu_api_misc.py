@@ -229,3 +229,17 @@ def test_statistics_and_decoder_entries_are_cuda_graph_capturable():
     e2, (S2, sv2, sh2) = s2.negative_phase()
     assert torch.equal(S1, S2) and torch.equal(sv1, sv2) and torch.equal(sh1, sh2)
     assert abs(e1.item() - e2.item()) <= 1e-5 * max(1.0, abs(e2.item()))
+
+
+def test_kernel_choice_by_shape():
+    """The shape-based choice inside the library, as bench.py reports it."""
+    lib = _lib.load()
+    name = lambda nV, nH, B, variant: lib.rbm_b200_kernel_choice(nV, nH, B, _lib.VARIANTS[variant]).decode()
+    assert name(64, 64, 100, "auto") == "smem_gibbs_kernel"                      # BASELINE configs[1]
+    assert name(256, 256, 1024, "auto") == "smem_gibbs_kernel"                   # configs[2]
+    assert name(1024, 1024, 65536, "auto") == "umma_half_step_kernel"            # configs[3] on one GPU
+    assert name(1024, 1024, 8192, "auto") == "umma_chain_kernel"                 # configs[3] sharded over 8 GPUs
+    assert name(512, 512, 2048, "umma") == "umma_resident_kernel"                # configs[4] shard at 8 GPUs
+    assert name(512, 512, 16384, "umma") == "umma_chain_kernel"                  # configs[4] on one GPU
+    assert name(512, 512, 2048, "umma_split") == "umma_chain_kernel"             # split weights: chain kernel only
+    assert name(1024, 1024, 64, "auto") in ("umma_chain_kernel", "umma_half_step_kernel")   # never the fp32 GENERAL path
