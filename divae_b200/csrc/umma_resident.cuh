@@ -12,9 +12,13 @@
 //     (one TMEM lane) and 32 units, i.e. exactly one 32-bit word, which it writes into every consumer CTA with
 //     st.async (... mbarrier::complete_tx): 8 KB per CTA and half-step instead of the 128 KB bf16 tile, no global
 //     memory, no flags, no polling - the consumer's mbarrier completes when the bytes have landed;
-//   * expander warps turn the words of one K block (128 chains x 64 units) into the SWIZZLE_128B bf16 A tile the
-//     tensor core reads, with one 16-byte table lookup per 8 units (a 4 KB table of the 256 byte patterns), into a
-//     3-stage ring; the MMA warp issues tcgen05.mma (M = 128, N = 64) as the K blocks appear;
+//   * expander warps turn the words of one K block (128 chains x 64 units) into bf16 {0,1} pairs in registers (shift +
+//     PRMT sign-replicate + AND: 2.5 ALU instructions per pair) and store them straight into TENSOR MEMORY
+//     (tcgen05.st: a thread owns one chain = one TMEM lane, a K block is 32 columns): the A operand of the MMAs is read
+//     from TMEM (tcgen05.mma with A in tensor memory), so the state never passes through shared memory as bf16 - no
+//     swizzled stores, no proxy fence, no A reads on the shared-memory port, and all 8 K blocks of a half-step have
+//     their own TMEM columns (a ring of 8 x 32 columns next to the two 64-column accumulators);
+//     the MMA warp issues tcgen05.mma (M = 128, N = 64, B = the resident W slice) as the K blocks appear;
 //   * the epilogue (tcgen05.ld -> bias, sigmoid, Philox, Bernoulli compare: the same arithmetic and draw contract as
 //     umma_common.cuh:epilogue_tile, so every kernel draws the same chains) produces the next words.
 // With two row blocks per cluster (ping-pong, two TMEM accumulators) the MMAs and the expansion of one block overlap
@@ -27,9 +31,15 @@ namespace rbm {
 namespace {
 
 constexpr int kResBN = 64;                 // output units per CTA and direction
-constexpr int kResStages = 3;              // A ring
+constexpr int kResStages = 8;              // A ring in tensor memory: 32 columns (64 bf16 units) per stage
+constexpr int kResAccCols = kResBN;        // one 64-column accumulator per row block
+constexpr int kResAColumn = 2 * kResAccCols;   // first TMEM column of the A ring (behind the accumulators of both slots)
 constexpr int kResEpiWarps = 8;            // warps 4..11: 4 TMEM lane quarters x 2 column sets of 32 units
-constexpr int kResExpWarps = 8;            // warps 12..19
+#ifndef RBM_RES_EXP_WARPS
+#define RBM_RES_EXP_WARPS 8
+#endif
+constexpr int kResExpWarps = RBM_RES_EXP_WARPS;   // warps 12..: groups of four (one per TMEM lane quarter) take K blocks in turn
+constexpr int kResExpGroups = kResExpWarps / 4;
 constexpr int kResThreads = 32 * (4 + kResEpiWarps + kResExpWarps);
 constexpr int kResMaxTiles = 8;            // portable cluster size
 constexpr int kResWBlockBytes = BLOCK_K * kResBN * 2;        // 8 KB: one K block of a W slice
@@ -55,7 +65,7 @@ struct ResidentArgs {
 };
 
 constexpr int kResStageBytes = 2 * 2 * kResEpiWarps * 128;   // [slot][use parity][epilogue warp][32 words]
-constexpr int kResPrologueBytes = 2 * kResExpWarps * 128;       // [slot][expander warp][32 words]
+constexpr int kResPrologueBytes = 2 * 8 * 128;       // [slot][expander warp < 8][32 words]
 
 // Latency tracing (debug builds only: RBM_B200_NVCC_DEFS=-DRBM_RES_TRACE): SM clock of the key events of a few
 // half-steps of CTA 0, read back through rbm_b200_debug_resident_trace().
@@ -78,7 +88,7 @@ __host__ __device__ inline ResidentSmem resident_smem(int tiles_h, int tiles_v) 
   s.w0 = 0;                                                  // K blocks of direction 0 = visible tiles
   s.w1 = s.w0 + (uint32_t)tiles_v * kResWBlockBytes;          // K blocks of direction 1 = hidden tiles
   s.ring = s.w1 + (uint32_t)tiles_h * kResWBlockBytes;
-  s.table = s.ring + kResStages * kABytes;
+  s.table = s.ring;                                          // (the A ring lives in tensor memory)
   s.bits = s.table + kResTableBytes;
   s.stage = s.bits + 4 * kResBitsBytes;                       // bits: [slot][parity]
   s.pro = s.stage + kResStageBytes;
@@ -98,6 +108,28 @@ __device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t se
   uint32_t d;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
   return d;
+}
+// 32 consecutive 32-bit columns of this thread's TMEM lane (lane = 32 * (warp % 4) + lane id)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] B[smem]: the A operand (M = 128 lanes x 8 columns = 16 bf16 of K per lane) is read from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -237,13 +269,13 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
   //  whole argument struct, into local memory)
   const bool act0 = j < args.n_tiles[0], act1 = j < args.n_tiles[1];     // this CTA computes units of direction 0 / 1
   const int nkb0 = args.n_tiles[1], nkb1 = args.n_tiles[0];              // K blocks read by direction 0 / 1
-  constexpr uint32_t kTmemCols = 2 * kResBN;
+  constexpr uint32_t kTmemCols = 512;   // 2 x 64 accumulator columns + 8 x 32 columns of A ring (power of two)
   const int n_pairs = ceil_div(ceil_div(args.row_blocks, args.slots), n_clusters);   // upper bound, same for every cluster
 
   if (warp_idx == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
   if (warp_idx == 1 && lane == 0) {
     mbar_init(w_full, 1);
-    for (int s = 0; s < kResStages; ++s) { mbar_init(ring_full(s), kResExpWarps / 2); mbar_init(ring_empty(s), 1); }
+    for (int s = 0; s < kResStages; ++s) { mbar_init(ring_full(s), 4); mbar_init(ring_empty(s), 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), kResEpiWarps);
       for (int par = 0; par < 2; ++par) {
@@ -303,7 +335,6 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
     mbar_wait(w_full, 0);
     int stage = 0; uint32_t phase = 0;
     uint32_t uses[2] = {0u, 0u};
-    const uint64_t adesc_base = make_smem_desc(smem_base + L.ring, 16, 1024);            // A: K-major
     const uint64_t bdesc0_base = make_smem_desc(smem_base + L.w0, BLOCK_K * 128, 1024);  // dir 0: MN-major
     const uint64_t bdesc1_base = make_smem_desc(smem_base + L.w1, 16, 1024);             // dir 1: K-major
     for (int pair = 0; pair < n_pairs; ++pair) {
@@ -316,7 +347,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             if (row_block(pair, s) < 0) continue;
             mbar_wait(tmem_empty(s), (uses[s] & 1u) ^ 1u);
             tcgen05_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(s * kResBN);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(s * kResAccCols);
             // Descriptors advance by ADDING to the 14-bit address field (all shared-memory addresses are below 256 KB, so
             // nothing carries out of it): ~35 instructions per K block instead of ~100 of descriptor arithmetic - with
             // 64-wide tiles a K block is only ~130 cycles of tensor time, the issue loop must not be longer.
@@ -328,10 +359,12 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
               tcgen05_fence_after();
               RES_TRACE(10 + kb, t, lane == 0 && s == 0);
               if (elect_one_sync()) {
-                const uint64_t adesc = adesc_base + (uint64_t)(stage * (kABytes >> 4));
+                const uint32_t a_tmem = tmem_base + (uint32_t)(kResAColumn + stage * 32);   // 4 x 8 columns: K = 16 each
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                  umma_bf16(tmem_d, adesc + (uint64_t)(k * ((UMMA_K * 2) >> 4)), bdesc + (uint64_t)k * bstep, idesc, (kb | k) != 0 ? 1u : 0u);
+                  // (splitting the accumulate chain over two accumulators - even / odd K steps - bought nothing:
+                  //  4.61 vs 4.45 us per half-step, profiles/r02_resident_vs_chain.txt)
+                  umma_bf16_ts(tmem_d, a_tmem + (uint32_t)(k * 8), bdesc + (uint64_t)k * bstep, idesc, (kb | k) != 0 ? 1u : 0u);
                 umma_commit(ring_empty(stage));
               }
               __syncwarp();
@@ -380,7 +413,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             const uint32_t par_full = uses[s] & 1u;
             auto wait_full = [&] { mbar_wait_long(tmem_full(s), par_full); RES_TRACE(20 + 4 * (warp_idx == 11), t, lane == 0 && s == 0 && (warp_idx == 4 || warp_idx == 11)); };
             auto release = [&] { mbar_arrive(tmem_empty(s)); RES_TRACE(21 + 4 * (warp_idx == 11), t, s == 0 && (warp_idx == 4 || warp_idx == 11)); };
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(s * kResBN);
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(s * kResAccCols);
             uint32_t bits;
             float wstep = 0.f;      // this half-step's 32-unit sum is added as ONE term, like the chain kernel's red
             if (dir == 0) bits = resident_epilogue<EPI0>(ep, tmem_acc, col0, chain, quarter, cq, lane, wstep, wait_full, release);
@@ -437,13 +470,14 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
     // ================================ expanders ================================
     const int e = warp_idx - 4 - kResEpiWarps;
     const int row = (e & 3) * 32 + lane;       // chain within the row block
-    const int half = e >> 2;                   // prologue: which 32 units of this CTA's 64; main loop: expander group
+    const int half = e >> 2;                   // prologue (warps e < 8): which 32 units of this CTA's 64
+    const int grp = e >> 2;                    // main loop: expander group
     const bool armer = (e == 0 && lane == 0);
     int stage = 0; uint32_t phase = 0;
     uint32_t bphase = 0;                       // bit (2 s + par): phase parity of bits_full(s, par) to wait for
     for (int pair = 0; pair < n_pairs; ++pair) {
       // prologue: this CTA's 64 units of the initial visible state -> words for the CTAs that compute direction 0
-      if (act1) {
+      if (act1 && e < 8) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           const int rb = row_block(pair, s);
@@ -460,7 +494,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
               if (wds[p] & 0xFFFF0000u) bits |= 1u << (8 * c + 2 * p + 1);
             }
           }
-          const uint32_t stg = smem_base + L.pro + (uint32_t)((s * kResExpWarps + e) * 128);
+          const uint32_t stg = smem_base + L.pro + (uint32_t)((s * 8 + e) * 128);
           st_shared_u32(stg + (uint32_t)lane * 4u, bits);
           fence_proxy_async_smem();
           __syncwarp();
@@ -485,7 +519,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
               // first, off the critical path
               int st2 = stage; uint32_t ph2 = phase;
               for (int kb = 0; kb < nkb && kb < kResStages; ++kb) {
-                if ((kb & 1) == half) mbar_wait(ring_empty(st2), ph2 ^ 1u);
+                if (kb % kResExpGroups == grp) mbar_wait(ring_empty(st2), ph2 ^ 1u);
                 if (++st2 == kResStages) { st2 = 0; ph2 ^= 1u; }
               }
             }
@@ -498,32 +532,33 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             // dependent chain of ~450 cycles: word load, PRMTs, stores, proxy fence, arrive); a warp covers 32
             // chains x 64 units = both words of its rows.
             for (int kb = 0; kb < nkb; ++kb) {
-              if ((kb & 1) == half) {
+              if (kb % kResExpGroups == grp) {
                 const uint32_t word0 = ld_shared_u32(bits_addr(s, par, 2 * kb, row));
                 const uint32_t word1 = ld_shared_u32(bits_addr(s, par, 2 * kb + 1, row));
                 if (kb >= kResStages) mbar_wait(ring_empty(stage), phase ^ 1u);   // (first slots: checked before the words came)
-                const uint32_t arow = smem_base + L.ring + stage * kABytes + (uint32_t)row * 128u;
+                tcgen05_fence_after();      // the MMAs that read this stage before have completed (commit -> ring_empty)
+                uint32_t o[32];             // column c of the stage = units 2c, 2c + 1 of the K block
 #pragma unroll
                 for (int hw = 0; hw < 2; ++hw) {
                   // 32 units -> 32 bf16 {0,1} in registers: vv[i] = word << (7 - i) carries unit 8c + i in the sign bit
                   // of byte c; PRMT in sign-replicate mode turns two such bytes into the masks of a bf16 pair, AND
-                  // 0x3F80 (2.5 ALU instructions per pair; a 256-entry table lookup cost a 10-way bank conflict)
+                  // 0x3F80 (2.5 ALU instructions per pair)
                   const uint32_t word = hw ? word1 : word0;
                   uint32_t vv[8];
 #pragma unroll
                   for (int i = 0; i < 8; ++i) vv[i] = word << (7 - i);
 #pragma unroll
                   for (int c = 0; c < 4; ++c) {
-                    uint32_t o[4];
 #pragma unroll
                     for (int pp = 0; pp < 4; ++pp) {
                       const uint32_t sel = (uint32_t)((8 | c) | ((8 | c) << 4) | ((12 | c) << 8) | ((12 | c) << 12));
-                      o[pp] = prmt_b32(vv[2 * pp], vv[2 * pp + 1], sel) & 0x3F803F80u;
+                      o[hw * 16 + c * 4 + pp] = prmt_b32(vv[2 * pp], vv[2 * pp + 1], sel) & 0x3F803F80u;
                     }
-                    st_shared_v4(arow + ((((uint32_t)(hw * 4 + c)) ^ ((uint32_t)row & 7u)) << 4), o[0], o[1], o[2], o[3]);
                   }
                 }
-                fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+                tmem_st32(tmem_base + ((uint32_t)((e & 3) * 32) << 16) + (uint32_t)(kResAColumn + stage * 32), o);
+                tmem_st_wait();
+                tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ring_full(stage));
                 RES_TRACE(1 + kb, t, (e & 3) == 0 && lane == 0 && s == 0);
