@@ -25,6 +25,8 @@
 // the epilogue of the other; with one the kernel runs at the latency of a single dependent half-step.
 // Clusters are independent of each other (chains are independent), so they need not be co-resident.
 #pragma once
+#include <mutex>
+
 #include "umma_chain.cuh"
 
 namespace rbm {
@@ -597,13 +599,15 @@ inline bool resident_supported(int nVp, int nHp) { return nVp <= kResMaxTiles * 
 // sm_count / cluster: 15 clusters of 8 on a 148-SM B200).  Queried once per (flavour, cluster size, shared-memory size).
 template <int EPI0, int EPI1>
 int resident_max_clusters(int cluster, int smem_bytes, int sm_count, int* out) {
-  static int cache[9][8] = {};   // [cluster size][smem size in 32 KB steps], 0 = not queried
+  static int cache[64][9][8] = {};   // [device][cluster size][smem size in 32 KB steps], 0 = not queried
+  static std::mutex mu;
   auto kern = umma_resident_kernel<EPI0, EPI1>;
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
   if ((rc = ensure_dynamic_smem(kern, di.device, smem_bytes))) return rc;
-  int& slot = cache[cluster][std::min(7, smem_bytes >> 15)];
+  std::lock_guard<std::mutex> lock(mu);
+  int& slot = cache[di.device & 63][cluster][std::min(7, smem_bytes >> 15)];
   if (slot == 0) {
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(kResThreads);
