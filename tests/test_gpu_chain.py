@@ -1,6 +1,7 @@
-"""The dataflow chain kernel (divae_b200/csrc/umma_chain.cuh): every tile shape (64 / 128 / 256 wide, CTA pairs) and
-the per-half-step launches of round 1 must draw the SAME chains (the draw contract is keyed by chain, unit and
-half-step, not by the tiling), and those chains must be the oracle's."""
+"""The dataflow chain kernel (divae_b200/csrc/umma_chain.cuh) in every tile shape (64 / 128 / 256 wide, CTA pairs), the
+resident kernel (umma_resident.cuh: one or two row blocks per cluster) and the per-half-step launches of round 1 must draw
+the SAME chains (the draw contract is keyed by chain, unit and half-step, not by the tiling or the kernel), and those
+chains must be the oracle's."""
 import os
 import subprocess
 import sys
@@ -14,7 +15,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CONFIGS = {
-    "auto": {},
+    "auto": {},                                                                  # resident kernel for the priors up to 512 x 512
+    "resident_one_block": {"RBM_B200_RESIDENT": "1", "RBM_B200_RESIDENT_SLOTS": "1"},
+    "resident_ping_pong": {"RBM_B200_RESIDENT": "1", "RBM_B200_RESIDENT_SLOTS": "2"},
     "launches": {"RBM_B200_CHAIN": "0"},
     "bn64": {"RBM_B200_CHAIN_BN": "64"},
     "bn128": {"RBM_B200_CHAIN_BN": "128"},
@@ -32,7 +35,7 @@ CONFIGS = {
     "bn64_opts0": {"RBM_B200_CHAIN_BN": "64", "RBM_B200_CHAIN_OPTS": "0"},
 }
 ENV_KEYS = ("RBM_B200_CHAIN", "RBM_B200_CHAIN_BN", "RBM_B200_CHAIN_PAIRS", "RBM_B200_CHAIN_GRID", "RBM_B200_CHAIN_SB",
-            "RBM_B200_CHAIN_OPTS")
+            "RBM_B200_CHAIN_OPTS", "RBM_B200_RESIDENT", "RBM_B200_RESIDENT_SLOTS")
 
 
 @pytest.fixture(scope="module")
@@ -43,6 +46,8 @@ def results(tmp_path_factory):
         env = dict(os.environ)
         for key in ENV_KEYS:
             env.pop(key, None)
+        if not name.startswith(("auto", "resident")):
+            env["RBM_B200_RESIDENT"] = "0"      # the chain-kernel configurations cover the small priors too
         env.update(extra)
         path = str(d / (name + ".npz"))
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "chain_env_worker.py"), path], env=env,
