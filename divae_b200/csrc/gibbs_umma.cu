@@ -455,7 +455,8 @@ int run_chain(const Plan& pl, uint16_t* Wp, uint16_t* Wlo, const float* nbh, con
   {
     const double items_per_cluster = (double)a.m_groups * std::min(a.n_tiles[0], a.n_tiles[1]) / std::max(1, sm_count / cfg.ctas);
     // (deferring a tile's last publication past the accumulator wait bought nothing: r02_chain_sweep5)
-    const int base = CHAIN_OPT_DEPWARP | CHAIN_OPT_CHUNKED | CHAIN_OPT_NO_WFENCE | CHAIN_OPT_NO_DEFER;
+    // (one gpu-scope release per chunk and CTA instead of one per epilogue warp: 15.7 vs 16.7 us per half-step at 8,192 chains)
+    const int base = CHAIN_OPT_DEPWARP | CHAIN_OPT_CHUNKED | CHAIN_OPT_NO_WFENCE | CHAIN_OPT_NO_DEFER | CHAIN_OPT_CTA_ARRIVE;
     a.opts = chain_opts_env >= 0 ? chain_opts_env
                                  : (items_per_cluster < 2.5 ? (base | CHAIN_OPT_MIDARRIVE) : (base | CHAIN_OPT_TILE_ARRIVE));
   }

@@ -63,7 +63,9 @@ enum { CHAIN_OPT_DEPWARP = 1,     // a dedicated warp polls the counters ahead o
        CHAIN_OPT_TILE_ARRIVE = 16,  // publish all chunks of a tile together when the tile is done
        CHAIN_OPT_ACQ_SPIN = 32,     // spin with ld.acquire (else relaxed loads + one final acquire)
        CHAIN_OPT_DEBUG_NOWAIT = 64, // TIMING EXPERIMENT ONLY (results invalid): publish without waiting for the stores
-       CHAIN_OPT_NO_DEFER = 128 };  // always publish a tile's last chunk at the accumulator wait (never defer it)
+       CHAIN_OPT_NO_DEFER = 128,    // always publish a tile's last chunk at the accumulator wait (never defer it)
+       CHAIN_OPT_CTA_ARRIVE = 256 };  // the epilogue warps of a CTA meet on a shared-memory counter and the LAST one publishes
+                                      // the chunk for all of them: one gpu-scope release per chunk and CTA instead of one per warp
 
 // Position in the item sequence of one cluster: items c, c + G, c + 2G, ... of the (super-block, t, tile) enumeration.
 struct ItemCursor {
@@ -155,9 +157,13 @@ __device__ __forceinline__ void st_release_cta_shared(uint32_t addr, uint32_t v)
 struct ChainHooks {
   uint32_t* pending;       // first counter of the chunks whose boxes this warp has handed to TMA but not yet published
   int n_pending;
+  uint32_t pending_slot;   // CTA_ARRIVE: shared-memory counter of the pending publication
   uint32_t* item_flags;    // counters of this item's first chunk
+  int cur_item;            // per-CTA index of the item item_flags belongs to
   int lane, n_groups;
-  bool at_mid, tile_arrive, wfence, nowait;
+  bool at_mid, tile_arrive, wfence, nowait, cta_arrive;
+  uint32_t cnt_base;       // CTA_ARRIVE: 8 shared-memory counters (4 items x 2 chunks in flight at most)
+  uint32_t arrivers;       // epilogue warps of this CTA that publish every chunk
   bool carried;            // `pending` belongs to the previous item (deferred at the accumulator wait)
   __device__ __forceinline__ void arrive() {
     if (pending != nullptr) {
@@ -165,11 +171,23 @@ struct ChainHooks {
       if (lane == 0) {
         if (!nowait) tma_store_wait_all();     // this warp's boxes of the new state are complete in global memory
         if (wfence) asm volatile("fence.proxy.async;" ::: "memory");
-        if (n_pending == 1) {
-          red_release_gpu_add(pending, 1u);
-        } else {
-          asm volatile("fence.acq_rel.gpu;" ::: "memory");
-          for (int i = 0; i < n_pending; ++i) red_relaxed_gpu_add(pending + i, 1u);
+        bool publish = true;
+        if (cta_arrive) {
+          // release this warp's completed stores to the CTA, acquire the earlier arrivers': the last warp's gpu-scope
+          // release below then covers the boxes of all of them (release/acquire chains are cumulative)
+          uint32_t old;
+          const uint32_t addr = cnt_base + 4u * pending_slot;
+          asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+          publish = old == arrivers - 1u;
+          if (publish) asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(0u) : "memory");
+        }
+        if (publish) {
+          if (n_pending == 1) {
+            red_release_gpu_add(pending, 1u);
+          } else {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            for (int i = 0; i < n_pending; ++i) red_relaxed_gpu_add(pending + i, 1u);
+          }
         }
       }
       pending = nullptr;
@@ -190,10 +208,12 @@ struct ChainHooks {
     if (tile_arrive) {
       if (pending != nullptr && pending != item_flags) arrive();   // (a carried tile is normally published at mid(0))
       pending = item_flags; n_pending = g + 1;
+      pending_slot = (uint32_t)((cur_item & 3) * 2);
     } else {
       // groups beyond the padded unit count skip before_store(): never overwrite an unpublished chunk
       if (pending != nullptr) arrive();
       pending = item_flags + g; n_pending = 1;
+      pending_slot = (uint32_t)((cur_item & 3) * 2 + g);
     }
   }
 };
@@ -239,6 +259,9 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::kBarOffset + 8 * (2 * kStages + 4));
   // number of dependency slots (in item order) the dependency warp has seen satisfied
   const uint32_t ready_seq = bar_base + 8u * (2 * kStages + 4) + 8u;
+  const uint32_t arrive_cnt = ready_seq + 8u;      // CTA_ARRIVE: 8 counters of 4 bytes
+  const bool cta_arrive = (args.opts & CHAIN_OPT_CTA_ARRIVE) != 0;
+  const uint32_t arrivals_per_write = cta_arrive ? 1u : (uint32_t)kArr;   // counter increments per chunk and half-step
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -263,6 +286,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), CTAS); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), kArr * CTAS); }
     st_release_cta_shared(ready_seq, 0u);
+    for (int i = 0; i < 8; ++i) st_release_cta_shared(arrive_cnt + 4u * i, 0u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp_idx == 2) {
@@ -300,7 +324,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
       const int nk = args.k_blocks[dir];
       const int nslots = KO::slots(nk);
       const int nt_prod = ceil_div(nk, KO::kTB);
-      const uint32_t need = it.writes_before(args) * (uint32_t)kArr;
+      const uint32_t need = it.writes_before(args) * arrivals_per_write;
       const uint32_t* dep_flags = args.flags + ((size_t)(dir ^ 1) * args.row_blocks + row_blk) * args.chunks_ld;
       const uint32_t lead_full_base = CTAS == 2 ? mapa_u32(full_bar(0), 0) : 0u;
       auto issue_b = [&](int kb, bool lo, int s) {
@@ -445,7 +469,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
       const int row_blk = it.m_grp(args) * CTAS + (int)cta_rank;
       const int nk = args.k_blocks[dir];
       const int nslots = KO::slots(nk);
-      const uint32_t need = it.writes_before(args) * (uint32_t)kArr;
+      const uint32_t need = it.writes_before(args) * arrivals_per_write;
       // counters of the state this item READS: written by direction dir ^ 1
       const uint32_t* flags = args.flags + ((size_t)(dir ^ 1) * args.row_blocks + row_blk) * args.chunks_ld;
       for (int q0 = 0; q0 < nslots; q0 += 32) {
@@ -484,6 +508,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
     hooks.wfence = (args.opts & CHAIN_OPT_NO_WFENCE) == 0;
     hooks.nowait = (args.opts & CHAIN_OPT_DEBUG_NOWAIT) != 0;
     hooks.carried = false;
+    hooks.cta_arrive = cta_arrive; hooks.cnt_base = arrive_cnt; hooks.arrivers = (uint32_t)kArr; hooks.cur_item = 0;
+    hooks.pending_slot = 0;
     const bool defer = (args.opts & CHAIN_OPT_NO_DEFER) == 0;
     int n = 0;
     ItemCursor it;
@@ -523,7 +549,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
       uint32_t* item_flags = args.flags + ((size_t)dir * args.row_blocks + row_blk) * args.chunks_ld + n_blk * KO::kGroups;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
       // (a deferred tile keeps its own counters in hooks.pending; item_flags is only used for the chunks stored from now on)
-      auto wait_full2 = [&] { wait_full(); hooks.item_flags = item_flags; };
+      auto wait_full2 = [&] { wait_full(); hooks.item_flags = item_flags; hooks.cur_item = n; };
       if (dir == 0)
         epilogue_tile<BLOCK_N, EPI0>(ep, &tm_o0, tmem_acc, n_blk, row_base, chain, quarter, cq, lane, stage_warp,
                                      EPI0 == EPI_AIS_WEIGHT ? args.wpart + (size_t)row * args.wpart_ld : nullptr,

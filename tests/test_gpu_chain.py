@@ -33,6 +33,10 @@ CONFIGS = {
     "bn256_opts4": {"RBM_B200_CHAIN_BN": "256", "RBM_B200_CHAIN_PAIRS": "0", "RBM_B200_CHAIN_OPTS": "4"},
     "bn128_opts141": {"RBM_B200_CHAIN_BN": "128", "RBM_B200_CHAIN_OPTS": "141"},
     "bn64_opts0": {"RBM_B200_CHAIN_BN": "64", "RBM_B200_CHAIN_OPTS": "0"},
+    # CTA-level arrival (bit 256): the last epilogue warp of a CTA publishes a chunk for all of them
+    "bn256_pairs_cta_arrive": {"RBM_B200_CHAIN_BN": "256", "RBM_B200_CHAIN_PAIRS": "1", "RBM_B200_CHAIN_OPTS": "399"},
+    "bn128_cta_arrive_tile": {"RBM_B200_CHAIN_BN": "128", "RBM_B200_CHAIN_OPTS": "413"},
+    "bn64_cta_arrive": {"RBM_B200_CHAIN_BN": "64", "RBM_B200_CHAIN_OPTS": "271"},
 }
 ENV_KEYS = ("RBM_B200_CHAIN", "RBM_B200_CHAIN_BN", "RBM_B200_CHAIN_PAIRS", "RBM_B200_CHAIN_GRID", "RBM_B200_CHAIN_SB",
             "RBM_B200_CHAIN_OPTS", "RBM_B200_RESIDENT", "RBM_B200_RESIDENT_SLOTS")
