@@ -20,7 +20,9 @@ Printed JSON (one line, rank 0):
   value         device-resident throughput: inputs (W, a, c) already in HBM, CUDA events around exactly K calls,
                 max over ranks; whole-job aggregate (all ranks' unit-updates / that time).
   e2e           the same metric through the public API with HOST buffers, over the same K steps: every step copies
-                the parameters host->device from pinned memory and the sampled (v, h) device->host.
+                the parameters host->device from pinned memory and the sampled (v, h) device->host (on a copy stream
+                into two alternating pinned buffers, so the read-back of step i overlaps the sampling of step i + 1;
+                the timed region ends after the last copy).
   roofline      tensor-pipe roofline of the dominant kernel: achieved = algorithmic flops of one rank's call
                 (2*B*nV*nH per half-step) / its measured duration, against MEASURED_PEAKS.json.
   negphase      second timed leg (gibbs): PCD.negative_phase() = chain (k = 20) + statistics GEMM + ONE flat NCCL
@@ -309,7 +311,7 @@ class Ctx:
             return t.item()
         return x
 
-    def timed(self, fn, steps, warmup, clocks=False):
+    def timed(self, fn, steps, warmup, clocks=False, before_stop=None):
         """ms per step: `warmup` untimed calls, then exactly `steps` calls between CUDA events on the current stream,
         barrier + synchronize on both sides, MAX over ranks."""
         torch = self.torch
@@ -324,6 +326,8 @@ class Ctx:
         e0.record()
         for _ in range(steps):
             fn()
+        if before_stop is not None:
+            before_stop()       # e.g. make the timing stream wait for copies issued on a side stream
         e1.record()
         self.barrier()
         ck = cs.stop() if cs else {}
@@ -405,8 +409,13 @@ def run_gibbs(args, ctx):
     W_host = rbm.weights.detach().cpu().pin_memory()
     a_host = rbm.visible_bias.detach().cpu().pin_memory()
     c_host = rbm.hidden_bias.detach().cpu().pin_memory()
-    v_host = torch.empty((chains, n), dtype=torch.float32).pin_memory()
-    h_host = torch.empty((chains, n), dtype=torch.float32).pin_memory()
+    # the user's loop: results go to the host on a copy stream (two pinned buffers), so the device->host read of step i
+    # overlaps the sampling of step i + 1; every copy is inside the timed region (the timing stream waits for the copy
+    # stream before the stop event)
+    v_host = [torch.empty((chains, n), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_host = [torch.empty((chains, n), dtype=torch.float32).pin_memory() for _ in range(2)]
+    main_stream, copy_stream = torch.cuda.current_stream(), torch.cuda.Stream()
+    state = {"i": 0}
 
     def e2e_step():
         with torch.no_grad():
@@ -414,11 +423,16 @@ def run_gibbs(args, ctx):
             rbm._visible_bias.copy_(a_host, non_blocking=True)
             rbm._hidden_bias.copy_(c_host, non_blocking=True)
         vv, hh = sampler.block_gibbs_sampling()
-        v_host.copy_(vv, non_blocking=True)
-        h_host.copy_(hh, non_blocking=True)
+        i = state["i"] = state["i"] + 1
+        copy_stream.wait_stream(main_stream)
+        with torch.cuda.stream(copy_stream):
+            v_host[i & 1].copy_(vv, non_blocking=True)
+            h_host[i & 1].copy_(hh, non_blocking=True)
+        vv.record_stream(copy_stream); hh.record_stream(copy_stream)
 
     e2e_steps = args.steps if args.e2e_steps <= 0 else max(1, min(args.steps, args.e2e_steps))
-    e2e_ms, _ = ctx.timed(e2e_step, e2e_steps, 1)
+    e2e_ms, _ = ctx.timed(e2e_step, e2e_steps, 1, before_stop=lambda: main_stream.wait_stream(copy_stream))
+    v_host = v_host[state["i"] & 1]
     h2d = 4 * (n * n + 2 * n)
     d2h = 4 * 2 * chains * n
     assert set(torch.unique(v_host[:256]).tolist()) <= {0.0, 1.0}
