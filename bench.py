@@ -228,12 +228,12 @@ def cpu_baseline(args):
                 "sample": "AIS in the reference's ATen style (the reference has no estimator) on RBM %dx%d, %d chains x %d betas"
                           % (n, n, chains, nb)}
     s = CpuSampler(n, args.cpu_chains, args.cpu_steps)
-    sweep = s.sweep()
+    sweep = s.sweep(repeats=3)
     best_t = min(sweep, key=sweep.get)
     units = unit_updates(args.cpu_chains, args.cpu_steps, n, n)
     return {"value": units / sweep[best_t], "unit": "unit-updates/s", "cores": best_t, "host_cpus": os.cpu_count(),
             "kind": s.kind, "thread_sweep": {str(t): units / sec for t, sec in sweep.items()},
-            "sample": "%s on RBM %dx%d, %d chains x %d steps, torch.no_grad, best of 2 per thread count, %.2f s per call at "
+            "sample": "%s on RBM %dx%d, %d chains x %d steps, torch.no_grad, warm-up + best of 3 per thread count, %.2f s per call at "
                       "%d threads" % (s.describe(), n, n, args.cpu_chains, args.cpu_steps, sweep[best_t], best_t)}
 
 
@@ -465,7 +465,12 @@ def run_gibbs(args, ctx):
         try:
             with open(tpath) as f:
                 tj = json.load(f)
-            traffic = tj.get("umma_chain_dram_bytes_per_half_step_8192" if chain_kernel else "umma_half_step_dram_bytes_per_launch")
+            if chain_kernel:
+                # one launch = the whole call (2k half-steps); measured per half-step at 8,192 chains (states stay in L2)
+                per_hs = tj.get("umma_chain_dram_bytes_per_half_step_8192")
+                traffic = per_hs * 2 * k if (per_hs is not None and chains == 8192 and n == 1024) else None
+            else:
+                traffic = tj.get("umma_half_step_dram_bytes_per_launch")
         except Exception:
             traffic = None
     default = (n, args.chains, k) == WORKLOADS["gibbs"][:3]

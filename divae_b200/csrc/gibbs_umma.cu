@@ -414,7 +414,11 @@ bool chain_enabled(int nVp, int nHp, int64_t rows_pad, int sm_count) {
   static const int max_items = env_int("RBM_B200_CHAIN_MAX_ITEMS", 10);
   const ChainCfg cfg = pick_chain_cfg(nVp, nHp, rows_pad, sm_count);
   const double items = (double)(rows_pad / (BLOCK_M * cfg.ctas)) * std::min(ceil_div(nVp, cfg.bn), ceil_div(nHp, cfg.bn));
-  return items < (double)max_items * std::max(1, sm_count / cfg.ctas);
+  // short K loops (priors below 512 units): an item is only 4 - 6 K blocks long and the dependency bookkeeping per item
+  // shows - 2.81 vs 2.26 ms per 100 steps at 256^2 x 16,384 chains, 6.09 vs 4.21 at 384^2 x 32,768 - so the chain kernel
+  // is kept to the few-items regime there (profiles/r02_chain_vs_launches.txt)
+  const double limit = std::max(nVp, nHp) < 512 ? 2.0 : (double)max_items;
+  return items < limit * std::max(1, sm_count / cfg.ctas);
 }
 
 // Launches the chain kernel over `steps` half-steps starting with direction 0.
