@@ -14,7 +14,8 @@ def main():
     res = {}
     rng = np.random.default_rng(123)
     for (nV, nH, B, k, scale) in ((1024, 1024, 700, 3, 0.03), (320, 192, 1500, 4, 0.1), (512, 512, 300, 5, 0.05),
-                                  (64, 64, 128, 2, 0.3), (130, 700, 260, 3, 0.05)):
+                                  (64, 64, 128, 2, 0.3), (130, 700, 260, 3, 0.05),
+                                  (256, 256, 4500, 2, 0.1)):      # 36 row blocks: more than one round of resident clusters
         W = (rng.standard_normal((nV, nH)) * scale).astype(np.float32)
         W = torch.from_numpy(W).to(torch.bfloat16).float().numpy()
         a = (0.5 + 0.2 * rng.standard_normal(nV)).astype(np.float32)
