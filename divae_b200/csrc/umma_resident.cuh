@@ -347,7 +347,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             if (row_block(pair, s) < 0) continue;
-            mbar_wait(tmem_empty(s), (uses[s] & 1u) ^ 1u);
+            mbar_wait_long(tmem_empty(s), (uses[s] & 1u) ^ 1u);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(s * kResAccCols);
             // Descriptors advance by ADDING to the 14-bit address field (all shared-memory addresses are below 256 KB, so
@@ -357,7 +357,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             const uint64_t bstep = dir ? (uint64_t)((UMMA_K * 2) >> 4) : (uint64_t)((UMMA_K * 128) >> 4);
             const uint32_t idesc = dir ? idesc1 : idesc0;
             for (int kb = 0; kb < nkb; ++kb) {
-              mbar_wait(ring_full(stage), phase);
+              mbar_wait_long(ring_full(stage), phase);
               tcgen05_fence_after();
               RES_TRACE(10 + kb, t, lane == 0 && s == 0);
               if (elect_one_sync()) {
@@ -521,7 +521,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
               // first, off the critical path
               int st2 = stage; uint32_t ph2 = phase;
               for (int kb = 0; kb < nkb && kb < kResStages; ++kb) {
-                if (kb % kResExpGroups == grp) mbar_wait(ring_empty(st2), ph2 ^ 1u);
+                if (kb % kResExpGroups == grp) mbar_wait_long(ring_empty(st2), ph2 ^ 1u);
                 if (++st2 == kResStages) { st2 = 0; ph2 ^= 1u; }
               }
             }
