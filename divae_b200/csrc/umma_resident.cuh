@@ -189,7 +189,7 @@ __device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint3
       __syncwarp();
       if (lane == 0) release();
     }
-    uint32_t amb = 0;          // units whose 16-bit field alone cannot decide (probability 2^-16 per draw)
+    bool amb = false;          // some unit's 16-bit field alone cannot decide (probability 2^-16 per draw)
     uint32_t half_bits = 0;
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
@@ -208,13 +208,16 @@ __device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint3
                                            : fmaf(__uint_as_float(r[c16]), ep.scale, nbv[i4] * ep.bmul);
         const Decision q = decision_terms(arg, kf);
         if (EPI == EPI_AIS_WEIGHT) {
+          // (no guard for the padding units of the last tile: their W columns and biases are zero padded, so arg = 0 and
+          //  the term is (0 - 0) + lg2(2) - lg2(2) = 0 exactly)
           const float ak = fminf(arg, 80.0f);
           const float akm1 = ak * ep.ratio;
-          if (col0 + cc < ep.n_valid)
-            wsum += (akm1 - ak) + lg2_approx(fminf(q.s, 1.2089258e24f)) - lg2_approx(1.0f + ex2_approx(akm1));
+          wsum += (akm1 - ak) + lg2_approx(fminf(q.s, 1.2089258e24f)) - lg2_approx(1.0f + ex2_approx(akm1));
         }
-        if (q.d >= q.s) half_bits |= 1u << c16;
-        if (__float_as_uint(q.d) < __float_as_uint(q.s)) amb |= 1u << c16;
+        // the unit's bit: one FSETP and one predicated OR (this kernel is bound by issued instructions)
+        asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
+            : "+r"(half_bits) : "f"(q.d), "f"(q.s), "r"(1u << c16));
+        amb = amb || (__float_as_uint(q.d) < __float_as_uint(q.s));
       }
     }
     if (amb) {
@@ -223,14 +226,15 @@ __device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint3
       // must stay short.
 #pragma unroll
       for (int c16 = 0; c16 < 16; ++c16) {
-        if ((amb >> c16) & 1u) {
-          const int cc = 16 * hh + c16;
-          const int b = (cc & 7) >> 1, slot = 2 * (cc >> 3) + (cc & 1);
-          const uint32_t word = w[b][slot >> 1];
-          const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
-          const float nbx = __ldg(ep.nbias + col0 + cc);
-          const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbx)
-                                             : fmaf(__uint_as_float(r[c16]), ep.scale, nbx * ep.bmul);
+        const int cc = 16 * hh + c16;
+        const int b = (cc & 7) >> 1, slot = 2 * (cc >> 3) + (cc & 1);
+        const uint32_t word = w[b][slot >> 1];
+        const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
+        const float nbx = __ldg(ep.nbias + col0 + cc);
+        const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbx)
+                                           : fmaf(__uint_as_float(r[c16]), ep.scale, nbx * ep.bmul);
+        const Decision q = decision_terms(arg, (float)k16);
+        if (__float_as_uint(q.d) < __float_as_uint(q.s)) {
           const uint32_t one = resolve_exact(arg, k16, ep.ctx, blk0 + b, chain, (uint32_t)slot);
           half_bits = (half_bits & ~(1u << c16)) | (one << c16);
         }
