@@ -32,7 +32,14 @@ names = {0: "words_in", 1: "exp_kb0", 2: "exp_kb1", 3: "exp_kb2", 4: "exp_kb3", 
          18: "mma_commit", 20: "epi4_acc", 21: "epi4_tmem_read", 22: "epi4_math", 23: "epi4_sent",
          24: "epi11_acc", 25: "epi11_tmem_read", 26: "epi11_math", 27: "epi11_sent"}
 print("rc", rc, "log Z", z)
-for t in range(1, 16):
-    base = a[t - 1][23] if a[t - 1][23] else a[t][0]
-    ev = sorted((int(a[t][k] - base), names[k]) for k in names if a[t][k])
+# events of slot s are recorded at index 32 s + event; offsets are SM cycles from the moment slot 0's words of half-step t arrived
+for t in range(1, 15):
+    base = a[t][0]
+    ev = []
+    for s in range(2):
+        for k in names:
+            for tt in (t, t + 1):
+                if a[tt][32 * s + k]:
+                    ev.append((int(a[tt][32 * s + k] - base), "t%d.s%d.%s" % (200 + tt, s, names[k])))
+    ev = sorted(x for x in ev if -2000 <= x[0] <= 14000)
     print("t=%d (dir %d): " % (200 + t, (200 + t) & 1) + "  ".join("%s %d" % (nm, dt) for dt, nm in ev))

@@ -204,8 +204,11 @@ __device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint3
         const uint32_t word = w[b][slot >> 1];
         const uint32_t mbits = (slot & 1) ? __byte_perm(word, ep.kf_magic, 0x7632) : __byte_perm(word, ep.kf_magic, 0x7610);
         const float kf = __uint_as_float(mbits) - 8388608.0f;
-        const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbv[i4])
-                                           : fmaf(__uint_as_float(r[c16]), ep.scale, nbv[i4] * ep.bmul);
+        // (the A operand holds 2.0 for a set unit, see the expanders: the accumulator is exactly twice the
+        //  pre-activation and the scale is halved - both are exact, so arg is bit for bit what the other kernels compute)
+        const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -0.5f * 1.4426950408889634f, nbv[i4])
+                          : EPI == EPI_ANNEALED ? fmaf(__uint_as_float(r[c16]), ep.scale, nbv[i4])
+                                                : fmaf(__uint_as_float(r[c16]), ep.scale, nbv[i4] * ep.bmul);
         const Decision q = decision_terms(arg, kf);
         if (EPI == EPI_AIS_WEIGHT) {
           // (no guard for the padding units of the last tile: their W columns and biases are zero padded, so arg = 0 and
@@ -231,8 +234,9 @@ __device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint3
         const uint32_t word = w[b][slot >> 1];
         const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
         const float nbx = __ldg(ep.nbias + col0 + cc);
-        const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -1.4426950408889634f, nbx)
-                                           : fmaf(__uint_as_float(r[c16]), ep.scale, nbx * ep.bmul);
+        const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -0.5f * 1.4426950408889634f, nbx)
+                          : EPI == EPI_ANNEALED ? fmaf(__uint_as_float(r[c16]), ep.scale, nbx)
+                                                : fmaf(__uint_as_float(r[c16]), ep.scale, nbx * ep.bmul);
         const Decision q = decision_terms(arg, (float)k16);
         if (__float_as_uint(q.d) < __float_as_uint(q.s)) {
           const uint32_t one = resolve_exact(arg, k16, ep.ctx, blk0 + b, chain, (uint32_t)slot);
@@ -248,6 +252,8 @@ __device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint3
 template <int EPI0, int EPI1>
 __global__ void __launch_bounds__(kResThreads, 1)
 umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArgs args) {
+  static_assert(EPI0 != EPI_ANNEALED, "EPI_ANNEALED is the direction-1 flavour here (bias multiplier 1)");
+  static_assert(kResStages == 8, "ring indexing assumes 8 stages");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -363,7 +369,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait_long(ring_full(stage), phase);
               tcgen05_fence_after();
-              RES_TRACE(10 + kb, t, lane == 0 && s == 0);
+              RES_TRACE(32 * s + 10 + kb, t, lane == 0);
               if (elect_one_sync()) {
                 const uint32_t a_tmem = tmem_base + (uint32_t)(kResAColumn + stage * 32);   // 4 x 8 columns: K = 16 each
 #pragma unroll
@@ -379,7 +385,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             }
             if (elect_one_sync()) umma_commit(tmem_full(s));
             __syncwarp();
-            RES_TRACE(18, t, lane == 0 && s == 0);
+            RES_TRACE(32 * s + 18, t, lane == 0);
             ++uses[s];
           }
         }
@@ -412,13 +418,13 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             ep.kf_magic = args.kf_magic;
             if (EPI0 != EPI_GIBBS) {
               const float bk = __ldg(args.betas + 1 + (t >> 1)), bkm1 = __ldg(args.betas + (t >> 1));
-              ep.scale = -1.4426950408889634f * bk;
-              ep.bmul = dir == 0 ? bk : 1.f;
+              ep.scale = 0.5f * (-1.4426950408889634f * bk);     // accumulators are doubled (A = 2.0 per set unit)
+              ep.bmul = dir == 0 ? bk : 1.f;                     // (EPI_ANNEALED = direction 1 here: bias multiplier 1)
               ep.ratio = bkm1 / bk;
             }
             const uint32_t par_full = uses[s] & 1u;
-            auto wait_full = [&] { mbar_wait_long(tmem_full(s), par_full); RES_TRACE(20 + 4 * (warp_idx == 11), t, lane == 0 && s == 0 && (warp_idx == 4 || warp_idx == 11)); };
-            auto release = [&] { mbar_arrive(tmem_empty(s)); RES_TRACE(21 + 4 * (warp_idx == 11), t, s == 0 && (warp_idx == 4 || warp_idx == 11)); };
+            auto wait_full = [&] { mbar_wait_long(tmem_full(s), par_full); RES_TRACE(32 * s + 20 + 4 * (warp_idx == 11), t, lane == 0 && (warp_idx == 4 || warp_idx == 11)); };
+            auto release = [&] { mbar_arrive(tmem_empty(s)); RES_TRACE(32 * s + 21 + 4 * (warp_idx == 11), t, (warp_idx == 4 || warp_idx == 11)); };
             const uint32_t tmem_acc = tmem_base + (uint32_t)(s * kResAccCols);
             uint32_t bits;
             float wstep = 0.f;      // this half-step's 32-unit sum is added as ONE term, like the chain kernel's red
@@ -426,7 +432,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             else bits = resident_epilogue<EPI1>(ep, tmem_acc, col0, chain, quarter, cq, lane, wstep, wait_full, release);
             wsum[s] += wstep;
             __syncwarp();
-            RES_TRACE(22 + 4 * (warp_idx == 11), t, lane == 0 && s == 0 && (warp_idx == 4 || warp_idx == 11));
+            RES_TRACE(32 * s + 22 + 4 * (warp_idx == 11), t, lane == 0 && (warp_idx == 4 || warp_idx == 11));
             if (t + 1 < args.steps) {
               // This warp's 32 words (32 chains x 32 units) go to every CTA that computes the next half-step: staged in
               // local shared memory, then ONE 128-byte bulk copy per destination (one complete_tx on its barrier;
@@ -445,7 +451,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
                 if (lane < n_dst) dsmem_bulk_copy(mapa_u32(dst, (uint32_t)lane), stg, 128u, mapa_u32(bar, (uint32_t)lane));
               }
               __syncwarp();
-              RES_TRACE(23 + 4 * (warp_idx == 11), t, lane == 0 && s == 0 && (warp_idx == 4 || warp_idx == 11));
+              RES_TRACE(32 * s + 23 + 4 * (warp_idx == 11), t, lane == 0 && (warp_idx == 4 || warp_idx == 11));
             }
             ++uses[s];
             if (t + 2 >= args.steps) {
@@ -479,7 +485,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
     const int half = e >> 2;                   // prologue (warps e < 8): which 32 units of this CTA's 64
     const int grp = e >> 2;                    // main loop: expander group
     const bool armer = (e == 0 && lane == 0);
-    int stage = 0; uint32_t phase = 0;
+    uint32_t ring_pos = 0;                     // K blocks expanded so far: block i of the ring sequence uses stage i % 8, phase (i / 8) & 1
     uint32_t bphase = 0;                       // bit (2 s + par): phase parity of bits_full(s, par) to wait for
     for (int pair = 0; pair < n_pairs; ++pair) {
       // prologue: this CTA's 64 units of the initial visible state -> words for the CTAs that compute direction 0
@@ -520,57 +526,53 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
           for (int s = 0; s < 2; ++s) {
             if (row_block(pair, s) < 0) continue;
             const uint32_t bit = 1u << (2 * s + par);
-            {
-              // the first ring slots of this half-step are normally free long before its words arrive: wait for them
-              // first, off the critical path
-              int st2 = stage; uint32_t ph2 = phase;
-              for (int kb = 0; kb < nkb && kb < kResStages; ++kb) {
-                if (kb % kResExpGroups == grp) mbar_wait_long(ring_empty(st2), ph2 ^ 1u);
-                if (++st2 == kResStages) { st2 = 0; ph2 ^= 1u; }
-              }
+            // The ring slots of this half-step (nkb <= 8 distinct stages) are normally free long before its words arrive:
+            // wait for this group's slots first, off the critical path.
+            for (int kb = grp; kb < nkb; kb += kResExpGroups) {
+              const uint32_t idx = ring_pos + (uint32_t)kb;
+              mbar_wait_long(ring_empty((int)(idx & (kResStages - 1))), ((idx >> 3) & 1u) ^ 1u);
             }
             mbar_wait_long(bits_full(s, par), (bphase & bit) ? 1u : 0u);
             bphase ^= bit;
-            RES_TRACE(0, t, e == 0 && lane == 0 && s == 0);
+            RES_TRACE(32 * s + 0, t, e == 0 && lane == 0);
             // re-arm for the next use of this (slot, parity): same direction, same byte count
             if (armer) mbar_arrive_expect_tx(bits_full(s, par), (uint32_t)nkb * 2u * BLOCK_M * 4u);
-            // Two groups of four warps expand alternate K blocks concurrently (the expansion of a K block is a
-            // dependent chain of ~450 cycles: word load, PRMTs, stores, proxy fence, arrive); a warp covers 32
-            // chains x 64 units = both words of its rows.
-            for (int kb = 0; kb < nkb; ++kb) {
-              if (kb % kResExpGroups == grp) {
-                const uint32_t word0 = ld_shared_u32(bits_addr(s, par, 2 * kb, row));
-                const uint32_t word1 = ld_shared_u32(bits_addr(s, par, 2 * kb + 1, row));
-                if (kb >= kResStages) mbar_wait(ring_empty(stage), phase ^ 1u);   // (first slots: checked before the words came)
-                tcgen05_fence_after();      // the MMAs that read this stage before have completed (commit -> ring_empty)
-                uint32_t o[32];             // column c of the stage = units 2c, 2c + 1 of the K block
+            tcgen05_fence_after();          // the MMAs that read these stages before have completed (commit -> ring_empty)
+            // The groups of four warps expand alternate K blocks concurrently; a warp covers 32 chains x 64 units = both
+            // words of its rows.
+            for (int kb = grp; kb < nkb; kb += kResExpGroups) {
+              const uint32_t word0 = ld_shared_u32(bits_addr(s, par, 2 * kb, row));
+              const uint32_t word1 = ld_shared_u32(bits_addr(s, par, 2 * kb + 1, row));
+              const int stage = (int)((ring_pos + (uint32_t)kb) & (kResStages - 1));
+              uint32_t o[32];             // column c of the stage = units 2c, 2c + 1 of the K block
 #pragma unroll
-                for (int hw = 0; hw < 2; ++hw) {
-                  // 32 units -> 32 bf16 {0,1} in registers: vv[i] = word << (7 - i) carries unit 8c + i in the sign bit
-                  // of byte c; PRMT in sign-replicate mode turns two such bytes into the masks of a bf16 pair, AND
-                  // 0x3F80 (2.5 ALU instructions per pair)
-                  const uint32_t word = hw ? word1 : word0;
-                  uint32_t vv[8];
+              for (int hw = 0; hw < 2; ++hw) {
+                // 32 units -> 32 bf16 {0, 2} in registers, ONE ALU instruction per unit.  A set unit becomes 2.0 = 0x4000:
+                // a single bit of the high byte, so m[i] = (word << (6 - i)) & 0x40404040 holds the high bytes of units
+                // 8c + i (c = 0..3) and one PRMT per bf16 pair picks them (selector nibbles with bit 3 replicate the sign
+                // bit of a byte whose top bit is clear: the zero low bytes).  The epilogue halves its scale - exact.
+                const uint32_t word = hw ? word1 : word0;
+                uint32_t m[8];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) vv[i] = word << (7 - i);
+                for (int i = 0; i < 7; ++i) m[i] = (word << (6 - i)) & 0x40404040u;
+                m[7] = (word >> 1) & 0x40404040u;
 #pragma unroll
-                  for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 4; ++c) {
 #pragma unroll
-                    for (int pp = 0; pp < 4; ++pp) {
-                      const uint32_t sel = (uint32_t)((8 | c) | ((8 | c) << 4) | ((12 | c) << 8) | ((12 | c) << 12));
-                      o[hw * 16 + c * 4 + pp] = prmt_b32(vv[2 * pp], vv[2 * pp + 1], sel) & 0x3F803F80u;
-                    }
+                  for (int pp = 0; pp < 4; ++pp) {
+                    const uint32_t sel = (uint32_t)((8 | c) | (c << 4) | ((12 | c) << 8) | ((4 | c) << 12));
+                    o[hw * 16 + c * 4 + pp] = prmt_b32(m[2 * pp], m[2 * pp + 1], sel);
                   }
                 }
-                tmem_st32(tmem_base + ((uint32_t)((e & 3) * 32) << 16) + (uint32_t)(kResAColumn + stage * 32), o);
-                tmem_st_wait();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ring_full(stage));
-                RES_TRACE(1 + kb, t, (e & 3) == 0 && lane == 0 && s == 0);
               }
-              if (++stage == kResStages) { stage = 0; phase ^= 1u; }
+              tmem_st32(tmem_base + ((uint32_t)((e & 3) * 32) << 16) + (uint32_t)(kResAColumn + stage * 32), o);
+              tmem_st_wait();
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(ring_full(stage));
+              RES_TRACE(32 * s + 1 + kb, t, (e & 3) == 0 && lane == 0);
             }
+            ring_pos += (uint32_t)nkb;
           }
         }
       }
