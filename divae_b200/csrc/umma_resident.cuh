@@ -26,6 +26,7 @@
 // Clusters are independent of each other (chains are independent), so they need not be co-resident.
 #pragma once
 #include <mutex>
+#include <type_traits>
 
 #include "umma_chain.cuh"
 
@@ -189,7 +190,8 @@ __device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint3
       __syncwarp();
       if (lane == 0) release();
     }
-    bool amb = false;          // some unit's 16-bit field alone cannot decide (probability 2^-16 per draw)
+    // ambq[q4]: some unit of the 4-unit group q4 cannot be decided by its 16-bit field alone (probability 2^-16 per draw)
+    bool ambq[4] = {false, false, false, false};
     uint32_t half_bits = 0;
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
@@ -220,27 +222,33 @@ __device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint3
         // the unit's bit: one FSETP and one predicated OR (this kernel is bound by issued instructions)
         asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
             : "+r"(half_bits) : "f"(q.d), "f"(q.s), "r"(1u << c16));
-        amb = amb || (__float_as_uint(q.d) < __float_as_uint(q.s));
+        ambq[q4] = ambq[q4] || (__float_as_uint(q.d) < __float_as_uint(q.s));
       }
     }
-    if (amb) {
+    if (ambq[0] || ambq[1] || ambq[2] || ambq[3]) {
       // Only the ambiguous units go through the exact path (for every other unit it returns what the fast path
-      // decided): in this kernel a whole cluster waits for its slowest warp every half-step, so the rare path
-      // must stay short.
+      // decided), and only the 4-unit groups that flagged are looked at: in this kernel a whole cluster waits for its
+      // slowest warp every half-step and SOME warp of a 512-unit cluster takes this path in 63 % of the half-steps, so
+      // the rare path must stay short (it was ~1,800 cycles when it re-examined all 16 units: res_trace_*_v6.txt).
 #pragma unroll
-      for (int c16 = 0; c16 < 16; ++c16) {
-        const int cc = 16 * hh + c16;
-        const int b = (cc & 7) >> 1, slot = 2 * (cc >> 3) + (cc & 1);
-        const uint32_t word = w[b][slot >> 1];
-        const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
-        const float nbx = __ldg(ep.nbias + col0 + cc);
-        const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -0.5f * 1.4426950408889634f, nbx)
-                          : EPI == EPI_ANNEALED ? fmaf(__uint_as_float(r[c16]), ep.scale, nbx)
-                                                : fmaf(__uint_as_float(r[c16]), ep.scale, nbx * ep.bmul);
-        const Decision q = decision_terms(arg, (float)k16);
-        if (__float_as_uint(q.d) < __float_as_uint(q.s)) {
-          const uint32_t one = resolve_exact(arg, k16, ep.ctx, blk0 + b, chain, (uint32_t)slot);
-          half_bits = (half_bits & ~(1u << c16)) | (one << c16);
+      for (int q4 = 0; q4 < 4; ++q4) {
+        if (!ambq[q4]) continue;
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int c16 = 4 * q4 + i4;
+          const int cc = 16 * hh + c16;
+          const int b = (cc & 7) >> 1, slot = 2 * (cc >> 3) + (cc & 1);
+          const uint32_t word = w[b][slot >> 1];
+          const uint32_t k16 = (slot & 1) ? (word >> 16) : (word & 0xFFFFu);
+          const float nbx = __ldg(ep.nbias + col0 + cc);
+          const float arg = EPI == EPI_GIBBS ? fmaf(__uint_as_float(r[c16]), -0.5f * 1.4426950408889634f, nbx)
+                            : EPI == EPI_ANNEALED ? fmaf(__uint_as_float(r[c16]), ep.scale, nbx)
+                                                  : fmaf(__uint_as_float(r[c16]), ep.scale, nbx * ep.bmul);
+          const Decision q = decision_terms(arg, (float)k16);
+          if (__float_as_uint(q.d) < __float_as_uint(q.s)) {
+            const uint32_t one = resolve_exact(arg, k16, ep.ctx, blk0 + b, chain, (uint32_t)slot);
+            half_bits = (half_bits & ~(1u << c16)) | (one << c16);
+          }
         }
       }
     }
@@ -342,51 +350,75 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
     for (int pair = 0; pair < n_pairs; ++pair) cluster_sync_all();
   } else if (warp_idx == 1) {
     // ================================ MMA issuer ================================
-    constexpr uint32_t idesc0 = make_idesc(BLOCK_M, kResBN, true);    // dir 0: B MN-major
-    constexpr uint32_t idesc1 = make_idesc(BLOCK_M, kResBN, false);   // dir 1: B K-major
     mbar_wait(w_full, 0);
-    int stage = 0; uint32_t phase = 0;
+    uint32_t ring_pos = 0;                  // K blocks issued so far: block i of the sequence uses stage i % 8, phase (i / 8) & 1
     uint32_t uses[2] = {0u, 0u};
     const uint64_t bdesc0_base = make_smem_desc(smem_base + L.w0, BLOCK_K * 128, 1024);  // dir 0: MN-major
     const uint64_t bdesc1_base = make_smem_desc(smem_base + L.w1, 16, 1024);             // dir 1: K-major
-    for (int pair = 0; pair < n_pairs; ++pair) {
-      for (int t = 0; t < args.steps; ++t) {
-        const int dir = t & 1;
-        const int nkb = dir ? nkb1 : nkb0;
-        if (dir ? act1 : act0) {
+    // One half-step of one row block.  With 64-wide tiles a K block is only ~130 cycles of tensor time, so the issue loop
+    // must not be longer: the direction is a compile-time constant and the loop over the (at most 8) K blocks is fully
+    // unrolled, so every descriptor is a uniform base plus an immediate (descriptors advance by ADDING to the 14-bit
+    // address field: all shared-memory addresses are below 256 KB, nothing carries out of it).  The rolled loop with
+    // run-time strides took ~45 instructions / ~340 cycles per K block (13 vector -> uniform register moves) and was the
+    // longest single stretch of a half-step (gpurun_out/res_trace_*_v6.txt).
+    auto issue = [&](auto dir_c, int s, int t) {
+      constexpr int DIR = decltype(dir_c)::value;
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, kResBN, DIR == 0);
+      constexpr uint64_t bstep = DIR ? (uint64_t)((UMMA_K * 2) >> 4) : (uint64_t)((UMMA_K * 128) >> 4);
+      const int nkb = DIR ? nkb1 : nkb0;
+      const uint64_t bdesc = DIR ? bdesc1_base : bdesc0_base;
+      mbar_wait_long(tmem_empty(s), (uses[s] & 1u) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(s * kResAccCols);
+      // K blocks are issued two at a time: the tensor pipe needs ~150 cycles for the four N = 64 MMAs of a K block
+      // (benchmarks/probes/ts_mma_probe.cu: 32 of them complete in 1,200 cycles) but one trip through this loop (barrier
+      // wait, elect, descriptors into uniform registers) costs ~190 cycles that do not overlap them, and the expanders
+      // run well ahead of the MMAs anyway (two groups finish K blocks 0 and 1 together).
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            if (row_block(pair, s) < 0) continue;
-            mbar_wait_long(tmem_empty(s), (uses[s] & 1u) ^ 1u);
-            tcgen05_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(s * kResAccCols);
-            // Descriptors advance by ADDING to the 14-bit address field (all shared-memory addresses are below 256 KB, so
-            // nothing carries out of it): ~35 instructions per K block instead of ~100 of descriptor arithmetic - with
-            // 64-wide tiles a K block is only ~130 cycles of tensor time, the issue loop must not be longer.
-            uint64_t bdesc = dir ? bdesc1_base : bdesc0_base;
-            const uint64_t bstep = dir ? (uint64_t)((UMMA_K * 2) >> 4) : (uint64_t)((UMMA_K * 128) >> 4);
-            const uint32_t idesc = dir ? idesc1 : idesc0;
-            for (int kb = 0; kb < nkb; ++kb) {
-              mbar_wait_long(ring_full(stage), phase);
-              tcgen05_fence_after();
-              RES_TRACE(32 * s + 10 + kb, t, lane == 0);
-              if (elect_one_sync()) {
-                const uint32_t a_tmem = tmem_base + (uint32_t)(kResAColumn + stage * 32);   // 4 x 8 columns: K = 16 each
+      for (int kb = 0; kb < kResMaxTiles; kb += 2) {
+        if (kb < nkb) {
+          const bool two = kb + 1 < nkb;
+          const uint32_t idx = ring_pos + (uint32_t)kb;
+          const uint32_t stage0 = idx & (uint32_t)(kResStages - 1), stage1 = (idx + 1u) & (uint32_t)(kResStages - 1);
+          mbar_wait_long(ring_full((int)stage0), (idx >> 3) & 1u);
+          if (two) mbar_wait_long(ring_full((int)stage1), ((idx + 1u) >> 3) & 1u);
+          tcgen05_fence_after();
+          RES_TRACE(32 * s + 10 + kb, t, lane == 0);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (h == 0 || two) {
+                const uint32_t stage = h ? stage1 : stage0;
+                const uint32_t a_tmem = tmem_base + (uint32_t)kResAColumn + stage * 32u;   // 4 x 8 columns: K = 16 each
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                   // (splitting the accumulate chain over two accumulators - even / odd K steps - bought nothing:
                   //  4.61 vs 4.45 us per half-step, profiles/r02_resident_vs_chain.txt)
-                  umma_bf16_ts(tmem_d, a_tmem + (uint32_t)(k * 8), bdesc + (uint64_t)k * bstep, idesc, (kb | k) != 0 ? 1u : 0u);
-                umma_commit(ring_empty(stage));
+                  umma_bf16_ts(tmem_d, a_tmem + (uint32_t)(k * 8),
+                               bdesc + (uint64_t)((kb + h) * (kResWBlockBytes >> 4)) + (uint64_t)k * bstep, idesc,
+                               (kb | h | k) != 0 ? 1u : 0u);
+                umma_commit(ring_empty((int)stage));
               }
-              __syncwarp();
-              bdesc += (uint64_t)(kResWBlockBytes >> 4);
-              if (++stage == kResStages) { stage = 0; phase ^= 1u; }
             }
-            if (elect_one_sync()) umma_commit(tmem_full(s));
-            __syncwarp();
-            RES_TRACE(32 * s + 18, t, lane == 0);
-            ++uses[s];
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one_sync()) umma_commit(tmem_full(s));
+      __syncwarp();
+      RES_TRACE(32 * s + 18, t, lane == 0);
+      ring_pos += (uint32_t)nkb;
+      ++uses[s];
+    };
+    for (int pair = 0; pair < n_pairs; ++pair) {
+      for (int t = 0; t < args.steps; ++t) {
+        const int dir = t & 1;
+        if (dir ? act1 : act0) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (row_block(pair, s) < 0) continue;
+            if (dir) issue(std::integral_constant<int, 1>{}, s, t);
+            else issue(std::integral_constant<int, 0>{}, s, t);
           }
         }
       }
@@ -444,11 +476,16 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
               fence_proxy_async_smem();
               __syncwarp();
               {
-                // lane d serves destination CTA d
+                // one elected lane issues the copies to all destination CTAs back to back (per-lane issue compiles to a
+                // serialised loop of 8 instructions per copy: the operands must be moved to uniform registers lane by lane)
                 const uint32_t dst = bits_addr(s, par, 2 * j + cq, quarter * 32);
                 const uint32_t bar = bits_full(s, par);
                 const int n_dst = dir ? args.n_tiles[0] : args.n_tiles[1];
-                if (lane < n_dst) dsmem_bulk_copy(mapa_u32(dst, (uint32_t)lane), stg, 128u, mapa_u32(bar, (uint32_t)lane));
+                if (elect_one_sync()) {
+#pragma unroll
+                  for (int d = 0; d < kResMaxTiles; ++d)
+                    if (d < n_dst) dsmem_bulk_copy(mapa_u32(dst, (uint32_t)d), stg, 128u, mapa_u32(bar, (uint32_t)d));
+                }
               }
               __syncwarp();
               RES_TRACE(32 * s + 23 + 4 * (warp_idx == 11), t, lane == 0 && (warp_idx == 4 || warp_idx == 11));
