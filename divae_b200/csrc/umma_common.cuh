@@ -225,6 +225,44 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// AIS log-weight of the hidden units, FOUR units at a time (the innermost loop of every epilogue runs over 4 consecutive
+// units).  Per unit the term is log p*_k(v) - log p*_{k-1}(v) = softplus(b_k x) - softplus(b_{k-1} x), in log2 units
+// (a' - a) + lg2(1 + 2^a) - lg2(1 + 2^a') with a = arg = -log2(e) b_k x and a' = a * b_{k-1} / b_k.  Taking the two
+// logarithms of every unit made the weight half-steps MUFU-bound (4 MUFU per unit with the sampler's own ex2: 16 lanes per
+// clock and SM); here the four (1 + 2^a) and the four (1 + 2^a') are multiplied up and the two logarithms are taken per
+// QUAD: 2.5 MUFU per unit (ex2 of a', half a lg2).  a is clamped at 30, where softplus(-x) = lg2(1 + 2^-a) < 1.4e-9 has
+// vanished in fp32 anyway, so a product of four factors stays below 2^121.
+// Padding units need no guard: their W columns and biases are zero padded, a = a' = 0, both factors are exactly 2 and
+// their logarithms cancel exactly.
+// (-DRBM_AIS_PER_UNIT_LOG restores the two logarithms per unit for accuracy comparisons: benchmarks/ais_weight_accuracy.py)
+struct AisQuad { float p, pm1, dsum; };
+__device__ __forceinline__ void ais_quad_add(AisQuad& q, int i4, float arg, float s, float ratio) {
+#ifdef RBM_AIS_PER_UNIT_LOG
+  const float ak80 = fminf(arg, 80.0f), akm80 = ak80 * ratio;
+  const float term = (akm80 - ak80) + lg2_approx(fminf(s, 1.2089258e24f)) - lg2_approx(1.0f + ex2_approx(akm80));
+  q.p = q.pm1 = 1.0f;
+  if (i4 == 0) q.dsum = term; else q.dsum += term;
+  return;
+#endif
+  const float ak = fminf(arg, 30.0f);
+  const float akm1 = ak * ratio;
+  const float sk = fminf(s, 1073741824.0f);          // 1 + 2^a, a <= 30 (s = 1 + 2^arg is +inf for arg > 128)
+  const float skm1 = 1.0f + ex2_approx(akm1);
+  if (i4 == 0) { q.p = sk; q.pm1 = skm1; q.dsum = akm1 - ak; }
+  else { q.p *= sk; q.pm1 *= skm1; q.dsum += akm1 - ak; }
+}
+// (lg2 of the QUOTIENT p * rcp.approx(pm1) would save nothing - rcp is a MUFU operation too - and rcp.approx is biased by
+//  about +2^-24 relative: measured +7.5e-6 nats per beta step on every chain's log-weight, 0.075 nats over the 10,000 betas
+//  of BASELINE configs[4] (benchmarks/ais_weight_accuracy.py, profiles/r02_ais_weight_accuracy.txt).  In the difference of
+//  the two logarithms the approximation errors of lg2 cancel: the arguments are within a factor 1 + O(d beta) of each other.)
+__device__ __forceinline__ float ais_quad_term(const AisQuad& q) { return q.dsum + (lg2_approx(q.p) - lg2_approx(q.pm1)); }
+
 // Decision rule shared by the fast path and the exact path (philox.cuh contract, p = 1/s):
 //   d = 65536 - k16 * s.   d >= s  <=>  (k16+1) * s <= 65536  <=>  p*65536 >= k16+1  -> 1
 //                          d <  0  <=>   k16 * s    >  65536  <=>  p*65536 <  k16    -> 0
@@ -359,6 +397,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
         for (int q4 = 0; q4 < 4; ++q4) {
           const float4 nb4 = __ldg(reinterpret_cast<const float4*>(ep.nbias + col0 + 16 * hh) + q4);
           const float nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+          AisQuad quad;
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
             const int c16 = 4 * q4 + i4;           // column within this 16-wide half
@@ -373,12 +412,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const CUtenso
                                                : fmaf(__uint_as_float(r[c16]), ep.scale, nbv[i4] * ep.bmul);
             const Decision q = decision_terms(arg, kf);
             if (EPI == EPI_AIS_WEIGHT) {
-              // log p*_k(v) - log p*_{k-1}(v), hidden-unit term: softplus(b_k x) - softplus(b_{k-1} x),
-              // in log2 units: softplus(bx)/ln2 = -arg + lg2(1 + 2^arg); clamped so 2^arg stays finite
-              const float ak = fminf(arg, 80.0f);
-              const float akm1 = ak * ep.ratio;
-              if (col0 + cc < ep.n_valid)
-                wsum += (akm1 - ak) + lg2_approx(fminf(q.s, 1.2089258e24f)) - lg2_approx(1.0f + ex2_approx(akm1));
+              // log p*_k(v) - log p*_{k-1}(v), hidden-unit term (ais_quad_add above), summed over the 4 units of q4
+              ais_quad_add(quad, i4, arg, q.s, ep.ratio);
+              if (i4 == 3) wsum += ais_quad_term(quad);
             }
             // fp32 1.0 / 0.0 straight from the compare (FSET); the top halves of two of them are the bf16 pair
             const uint32_t onef = __float_as_uint(q.d >= q.s ? 1.0f : 0.0f);

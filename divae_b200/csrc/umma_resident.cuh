@@ -163,6 +163,27 @@ __device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
   } while (!done);
 }
 
+// Long waits of a whole role (8 epilogue warps for an accumulator, 8 expander warps for the words of a half-step): only the
+// role's first warp polls the mbarrier, the others block on a named barrier.  A warp sleeping in try_wait is woken by
+// every mbarrier event of the SM (~160 times per half-step and row block here: bulk-copy completions, ring arrivals) and
+// re-checks - 10 % of all issued instructions of the ping-pong profile (profiles/r02_ncu_resident_v8_*), taken from the
+// warps that work; a warp blocked in bar.sync issues nothing.  MEASURED SLOWER (Gibbs 512 x 512: 3.10 vs 3.06 us per
+// half-step at 1,024 chains, 4.28 vs 4.13 at 2,048: the role then moves at the pace of its slowest warp) - off by default.
+#ifndef RBM_RES_LEADER_WAIT
+#define RBM_RES_LEADER_WAIT 0
+#endif
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void role_wait(uint32_t bar, uint32_t parity, bool leader, int bar_id, int threads) {
+#if RBM_RES_LEADER_WAIT
+  if (leader) mbar_wait_long(bar, parity);
+  named_bar_sync(bar_id, threads);
+#else
+  mbar_wait_long(bar, parity);
+#endif
+}
+
 // One epilogue warp, one half-step of one row block: 32 chains (lanes) x 32 units -> one 32-bit word per lane.
 // Same arithmetic as epilogue_tile (umma_common.cuh): arg = acc * scale + nbias * bmul, s = 1 + 2^arg,
 // d = 65536 - k16 s; fire iff d >= s; 0 <= d < s is re-done on the exact path.
@@ -197,6 +218,7 @@ __device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint3
     for (int q4 = 0; q4 < 4; ++q4) {
       const float4 nb4 = __ldg(reinterpret_cast<const float4*>(ep.nbias + col0 + 16 * hh) + q4);
       const float nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+      AisQuad quad;
 #pragma unroll
       for (int i4 = 0; i4 < 4; ++i4) {
         const int c16 = 4 * q4 + i4;
@@ -213,11 +235,10 @@ __device__ __forceinline__ uint32_t resident_epilogue(const EpiParams& ep, uint3
                                                 : fmaf(__uint_as_float(r[c16]), ep.scale, nbv[i4] * ep.bmul);
         const Decision q = decision_terms(arg, kf);
         if (EPI == EPI_AIS_WEIGHT) {
-          // (no guard for the padding units of the last tile: their W columns and biases are zero padded, so arg = 0 and
-          //  the term is (0 - 0) + lg2(2) - lg2(2) = 0 exactly)
-          const float ak = fminf(arg, 80.0f);
-          const float akm1 = ak * ep.ratio;
-          wsum += (akm1 - ak) + lg2_approx(fminf(q.s, 1.2089258e24f)) - lg2_approx(1.0f + ex2_approx(akm1));
+          // log-weight terms of the 4 units of q4 at a time (umma_common.cuh:ais_quad_add - the same arithmetic in the same
+          // order as the other kernels; padding units contribute exactly 0)
+          ais_quad_add(quad, i4, arg, q.s, ep.ratio);
+          if (i4 == 3) wsum += ais_quad_term(quad);
         }
         // the unit's bit: one FSETP and one predicated OR (this kernel is bound by issued instructions)
         asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}"
@@ -455,7 +476,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
               ep.ratio = bkm1 / bk;
             }
             const uint32_t par_full = uses[s] & 1u;
-            auto wait_full = [&] { mbar_wait_long(tmem_full(s), par_full); RES_TRACE(32 * s + 20 + 4 * (warp_idx == 11), t, lane == 0 && (warp_idx == 4 || warp_idx == 11)); };
+            auto wait_full = [&] { role_wait(tmem_full(s), par_full, warp_idx == 4, 1, 32 * kResEpiWarps); RES_TRACE(32 * s + 20 + 4 * (warp_idx == 11), t, lane == 0 && (warp_idx == 4 || warp_idx == 11)); };
             auto release = [&] { mbar_arrive(tmem_empty(s)); RES_TRACE(32 * s + 21 + 4 * (warp_idx == 11), t, (warp_idx == 4 || warp_idx == 11)); };
             const uint32_t tmem_acc = tmem_base + (uint32_t)(s * kResAccCols);
             uint32_t bits;
@@ -569,7 +590,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
               const uint32_t idx = ring_pos + (uint32_t)kb;
               mbar_wait_long(ring_empty((int)(idx & (kResStages - 1))), ((idx >> 3) & 1u) ^ 1u);
             }
-            mbar_wait_long(bits_full(s, par), (bphase & bit) ? 1u : 0u);
+            role_wait(bits_full(s, par), (bphase & bit) ? 1u : 0u, e == 0, 2, 32 * kResExpWarps);
             bphase ^= bit;
             RES_TRACE(32 * s + 0, t, e == 0 && lane == 0);
             // re-arm for the next use of this (slot, parity): same direction, same byte count
