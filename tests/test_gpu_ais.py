@@ -47,6 +47,24 @@ def test_ais_tracks_cpu_restatement_chain_by_chain():
     assert np.median(diff) < 5e-3 and (diff < 5e-2).mean() > 0.8
 
 
+def test_ais_log_weight_arithmetic_is_unbiased():
+    """Chains that follow the oracle's trajectory differ from it by fp32 / MUFU arithmetic only; the MEAN of that difference
+    is a bias every estimate inherits and it grows with the number of betas (a quotient form with rcp.approx was +7.5e-6 nats
+    per beta step at 512 hidden units: profiles/r02_ais_weight_accuracy.txt).  Checked on a prior the resident kernel
+    takes and on one the chain kernel takes."""
+    for (n, M, K) in ((128, 256, 300), (640, 256, 200)):      # 128 x 128: resident kernel; 640 x 640: chain kernel
+        W, a, c = small_rbm(n, n, 0.05, 21)
+        rbm = make_rbm(W, a, c)
+        betas = np.linspace(0, 1, K + 1)
+        _, logw = rbm.estimate_logZ(n_chains=M, betas=betas, seed=13, return_logw=True)
+        _, ref_logw, _ = orc.ais_logZ(W, a, c, M, betas, 13, return_logw=True)
+        d = logw.cpu().numpy() - ref_logw
+        clean = np.abs(d) < 0.02
+        assert clean.mean() > 0.8, (n, clean.mean())
+        # the rejected form would be at +5.6e-4 (128 units, 300 betas) / +1.9e-3 (640 units, 200 betas)
+        assert abs(d[clean].mean()) < 3e-4, (n, d[clean].mean())
+
+
 def test_ais_config5_shape_against_cpu_restatement():
     """BASELINE config 5 prior (2 x 512) with a reduced schedule; weights at trained-like scale."""
     W, a, c = small_rbm(512, 512, 0.02, 5)
