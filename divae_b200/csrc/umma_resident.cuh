@@ -96,7 +96,7 @@ __host__ __device__ inline ResidentSmem resident_smem(int tiles_h, int tiles_v) 
   s.stage = s.bits + 4 * kResBitsBytes;                       // bits: [slot][parity]
   s.pro = s.stage + kResStageBytes;
   s.bars = s.pro + kResPrologueBytes;
-  s.total = (int)s.bars + 256 + 1024;
+  s.total = (int)s.bars + 512 + 1024;
   return s;
 }
 
@@ -293,7 +293,9 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
   auto ring_empty = [&](int s) { return bar_base + 8u * (1 + kResStages + s); };
   auto tmem_full = [&](int s) { return bar_base + 8u * (1 + 2 * kResStages + s); };
   auto tmem_empty = [&](int s) { return bar_base + 8u * (3 + 2 * kResStages + s); };
-  auto bits_full = [&](int s, int par) { return bar_base + 8u * (5 + 2 * kResStages + 2 * s + par); };
+  // words of one K block = the 64 units CTA kb of the cluster wrote: one barrier per (slot, parity, source CTA), so a late
+  // CTA delays only its own K block (the whole cluster used to wait for its slowest warp before ANY expansion started)
+  auto bits_full = [&](int s, int par, int kb) { return bar_base + 8u * (10 + 2 * kResStages + (2 * s + par) * kResMaxTiles + kb); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L.bars + 8 * (9 + 2 * kResStages));
   auto bits_addr = [&](int s, int par, int word, int row) {
     return smem_base + L.bits + (uint32_t)(((s * 2 + par) * 16 + word) * BLOCK_M + row) * 4u;
@@ -320,9 +322,11 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), kResEpiWarps);
       for (int par = 0; par < 2; ++par) {
-        mbar_init(bits_full(s, par), 1);
-        // armed for its first use: the words of all K blocks of the direction that reads this parity
-        mbar_arrive_expect_tx(bits_full(s, par), (uint32_t)(par ? nkb1 : nkb0) * 2u * BLOCK_M * 4u);
+        for (int kb = 0; kb < (par ? nkb1 : nkb0); ++kb) {
+          mbar_init(bits_full(s, par, kb), 1);
+          // armed for its first use: the two words per chain of K block kb
+          mbar_arrive_expect_tx(bits_full(s, par, kb), 2u * BLOCK_M * 4u);
+        }
       }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -500,7 +504,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
                 // one elected lane issues the copies to all destination CTAs back to back (per-lane issue compiles to a
                 // serialised loop of 8 instructions per copy: the operands must be moved to uniform registers lane by lane)
                 const uint32_t dst = bits_addr(s, par, 2 * j + cq, quarter * 32);
-                const uint32_t bar = bits_full(s, par);
+                const uint32_t bar = bits_full(s, par, j);      // this CTA is K block j of its consumers
                 const int n_dst = dir ? args.n_tiles[0] : args.n_tiles[1];
                 if (elect_one_sync()) {
 #pragma unroll
@@ -542,9 +546,8 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
     const int row = (e & 3) * 32 + lane;       // chain within the row block
     const int half = e >> 2;                   // prologue (warps e < 8): which 32 units of this CTA's 64
     const int grp = e >> 2;                    // main loop: expander group
-    const bool armer = (e == 0 && lane == 0);
     uint32_t ring_pos = 0;                     // K blocks expanded so far: block i of the ring sequence uses stage i % 8, phase (i / 8) & 1
-    uint32_t bphase = 0;                       // bit (2 s + par): phase parity of bits_full(s, par) to wait for
+    uint32_t bphase = 0;                       // bit (2 s + par): phase parity of bits_full(s, par, *) to wait for
     for (int pair = 0; pair < n_pairs; ++pair) {
       // prologue: this CTA's 64 units of the initial visible state -> words for the CTAs that compute direction 0
       if (act1 && e < 8) {
@@ -570,7 +573,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
           __syncwarp();
           {
             const uint32_t dst = bits_addr(s, 0, 2 * j + half, (e & 3) * 32);
-            const uint32_t bar = bits_full(s, 0);
+            const uint32_t bar = bits_full(s, 0, j);
             if (lane < args.n_tiles[0]) dsmem_bulk_copy(mapa_u32(dst, (uint32_t)lane), stg, 128u, mapa_u32(bar, (uint32_t)lane));
           }
           __syncwarp();
@@ -590,15 +593,17 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
               const uint32_t idx = ring_pos + (uint32_t)kb;
               mbar_wait_long(ring_empty((int)(idx & (kResStages - 1))), ((idx >> 3) & 1u) ^ 1u);
             }
-            role_wait(bits_full(s, par), (bphase & bit) ? 1u : 0u, e == 0, 2, 32 * kResExpWarps);
+            const uint32_t bpar = (bphase & bit) ? 1u : 0u;
             bphase ^= bit;
-            RES_TRACE(32 * s + 0, t, e == 0 && lane == 0);
-            // re-arm for the next use of this (slot, parity): same direction, same byte count
-            if (armer) mbar_arrive_expect_tx(bits_full(s, par), (uint32_t)nkb * 2u * BLOCK_M * 4u);
             tcgen05_fence_after();          // the MMAs that read these stages before have completed (commit -> ring_empty)
             // The groups of four warps expand alternate K blocks concurrently; a warp covers 32 chains x 64 units = both
             // words of its rows.
             for (int kb = grp; kb < nkb; kb += kResExpGroups) {
+              mbar_wait_long(bits_full(s, par, kb), bpar);
+              RES_TRACE(32 * s + 0, t, e == 0 && lane == 0 && kb == 0);
+              // re-arm for the next use of this (slot, parity, K block): the next words cannot arrive before every warp of
+              // this CTA has passed this wait (they depend on this half-step's accumulator)
+              if ((e & 3) == 0 && lane == 0) mbar_arrive_expect_tx(bits_full(s, par, kb), 2u * BLOCK_M * 4u);
               const uint32_t word0 = ld_shared_u32(bits_addr(s, par, 2 * kb, row));
               const uint32_t word1 = ld_shared_u32(bits_addr(s, par, 2 * kb + 1, row));
               const int stage = (int)((ring_pos + (uint32_t)kb) & (kResStages - 1));
