@@ -9,16 +9,19 @@
 //       direction 1 (h -> v): W[64j : 64j+64, :]  as K blocks of [64 n x 64 k], K-major B operand
 //     (2 x 64 KB at 512 x 512 - there is no W traffic at all after the prologue);
 //   * the states travel between the CTAs as BIT WORDS over distributed shared memory: an epilogue lane owns one chain
-//     (one TMEM lane) and 32 units, i.e. exactly one 32-bit word, which it writes into every consumer CTA with
-//     st.async (... mbarrier::complete_tx): 8 KB per CTA and half-step instead of the 128 KB bf16 tile, no global
-//     memory, no flags, no polling - the consumer's mbarrier completes when the bytes have landed;
-//   * expander warps turn the words of one K block (128 chains x 64 units) into bf16 {0,1} pairs in registers (shift +
-//     PRMT sign-replicate + AND: 2.5 ALU instructions per pair) and store them straight into TENSOR MEMORY
+//     (one TMEM lane) and 32 units, i.e. exactly one 32-bit word; a warp stages its 32 words in local shared memory and
+//     issues ONE 128-byte cp.async.bulk.shared::cluster per consumer CTA (... mbarrier::complete_tx): 8 KB per CTA and
+//     half-step instead of the 128 KB bf16 tile, no global memory, no flags - the consumer has one mbarrier per SOURCE
+//     CTA (= per K block of its next half-step), which completes when that CTA's words have landed, so a late CTA delays
+//     only its own K block;
+//   * expander warps turn the words of one K block (128 chains x 64 units) into bf16 pairs in registers - a set unit
+//     becomes 2.0 = 0x4000, a single bit of the high byte: shift + AND per unit-byte, one PRMT per pair = ONE ALU
+//     instruction per unit; the epilogue halves its scale, both exact - and store them straight into TENSOR MEMORY
 //     (tcgen05.st: a thread owns one chain = one TMEM lane, a K block is 32 columns): the A operand of the MMAs is read
 //     from TMEM (tcgen05.mma with A in tensor memory), so the state never passes through shared memory as bf16 - no
 //     swizzled stores, no proxy fence, no A reads on the shared-memory port, and all 8 K blocks of a half-step have
 //     their own TMEM columns (a ring of 8 x 32 columns next to the two 64-column accumulators);
-//     the MMA warp issues tcgen05.mma (M = 128, N = 64, B = the resident W slice) as the K blocks appear;
+//     the MMA warp issues tcgen05.mma (M = 128, N = 64, B = the resident W slice) two K blocks per trip as they appear;
 //   * the epilogue (tcgen05.ld -> bias, sigmoid, Philox, Bernoulli compare: the same arithmetic and draw contract as
 //     umma_common.cuh:epilogue_tile, so every kernel draws the same chains) produces the next words.
 // With two row blocks per cluster (ping-pong, two TMEM accumulators) the MMAs and the expansion of one block overlap
