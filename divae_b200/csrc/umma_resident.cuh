@@ -153,6 +153,14 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 
 // mbarrier wait with a suspend-time hint: the waits of this kernel are long (a dependent half-step away) and every
 // spin of a waiting warp takes an issue slot from the expander / epilogue warps
+// RBM_RES_HINT: which waits carry the hint (bit 0: the epilogue's wait for the accumulator, bit 1: the MMA warp's waits,
+// bit 2: the expanders' waits).  In the single-block trace the epilogue sees the accumulator ~700 cycles after the commit
+// was issued, of which the tensor pipe accounts for ~300; un-hinted waits on the MMA and epilogue side (RBM_RES_HINT=4)
+// measured the same within noise (512 x 512: 2.81 vs 2.83 us per half-step at 1,024 chains, 4.03 vs 4.06 at 2,048), so
+// the wake-up of a hinted wait is not where that time goes.
+#ifndef RBM_RES_HINT
+#define RBM_RES_HINT 7
+#endif
 __device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -165,6 +173,11 @@ __device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+template <int BIT>
+__device__ __forceinline__ void mbar_wait_role(uint32_t bar, uint32_t parity) {
+  if ((RBM_RES_HINT >> BIT) & 1) mbar_wait_long(bar, parity); else mbar_wait(bar, parity);
+}
+
 
 // Long waits of a whole role (8 epilogue warps for an accumulator, 8 expander warps for the words of a half-step): only the
 // role's first warp polls the mbarrier, the others block on a named barrier.  A warp sleeping in try_wait is woken by
@@ -183,7 +196,7 @@ __device__ __forceinline__ void role_wait(uint32_t bar, uint32_t parity, bool le
   if (leader) mbar_wait_long(bar, parity);
   named_bar_sync(bar_id, threads);
 #else
-  mbar_wait_long(bar, parity);
+  mbar_wait_role<0>(bar, parity);
 #endif
 }
 
@@ -395,7 +408,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
       constexpr uint64_t bstep = DIR ? (uint64_t)((UMMA_K * 2) >> 4) : (uint64_t)((UMMA_K * 128) >> 4);
       const int nkb = DIR ? nkb1 : nkb0;
       const uint64_t bdesc = DIR ? bdesc1_base : bdesc0_base;
-      mbar_wait_long(tmem_empty(s), (uses[s] & 1u) ^ 1u);
+      mbar_wait_role<1>(tmem_empty(s), (uses[s] & 1u) ^ 1u);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(s * kResAccCols);
       // K blocks are issued two at a time: the tensor pipe needs ~150 cycles for the four N = 64 MMAs of a K block
@@ -408,8 +421,8 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
           const bool two = kb + 1 < nkb;
           const uint32_t idx = ring_pos + (uint32_t)kb;
           const uint32_t stage0 = idx & (uint32_t)(kResStages - 1), stage1 = (idx + 1u) & (uint32_t)(kResStages - 1);
-          mbar_wait_long(ring_full((int)stage0), (idx >> 3) & 1u);
-          if (two) mbar_wait_long(ring_full((int)stage1), ((idx + 1u) >> 3) & 1u);
+          mbar_wait_role<1>(ring_full((int)stage0), (idx >> 3) & 1u);
+          if (two) mbar_wait_role<1>(ring_full((int)stage1), ((idx + 1u) >> 3) & 1u);
           tcgen05_fence_after();
           RES_TRACE(32 * s + 10 + kb, t, lane == 0);
           if (elect_one_sync()) {
@@ -594,7 +607,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             // wait for this group's slots first, off the critical path.
             for (int kb = grp; kb < nkb; kb += kResExpGroups) {
               const uint32_t idx = ring_pos + (uint32_t)kb;
-              mbar_wait_long(ring_empty((int)(idx & (kResStages - 1))), ((idx >> 3) & 1u) ^ 1u);
+              mbar_wait_role<2>(ring_empty((int)(idx & (kResStages - 1))), ((idx >> 3) & 1u) ^ 1u);
             }
             const uint32_t bpar = (bphase & bit) ? 1u : 0u;
             bphase ^= bit;
@@ -602,7 +615,7 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             // The groups of four warps expand alternate K blocks concurrently; a warp covers 32 chains x 64 units = both
             // words of its rows.
             for (int kb = grp; kb < nkb; kb += kResExpGroups) {
-              mbar_wait_long(bits_full(s, par, kb), bpar);
+              mbar_wait_role<2>(bits_full(s, par, kb), bpar);
               RES_TRACE(32 * s + 0, t, e == 0 && lane == 0 && kb == 0);
               // re-arm for the next use of this (slot, parity, K block): the next words cannot arrive before every warp of
               // this CTA has passed this wait (they depend on this half-step's accumulator)
