@@ -70,7 +70,7 @@ struct ResidentArgs {
   __nv_bfloat16* out[2];         // final states: out[0] = hidden [rows_pad, ld[0]], out[1] = visible [rows_pad, ld[1]]
 };
 
-constexpr int kResStageBytes = 2 * 2 * kResEpiWarps * 128;   // [slot][use parity][epilogue warp][32 words]
+constexpr int kResStageBytes = 2 * 2 * 1024;   // [slot][use parity][word 0 / 1 of this CTA][128 chains]
 constexpr int kResPrologueBytes = 2 * 8 * 128;       // [slot][expander warp < 8][32 words]
 
 // Latency tracing (debug builds only: RBM_B200_NVCC_DEFS=-DRBM_RES_TRACE): SM clock of the key events of a few
@@ -507,28 +507,28 @@ umma_resident_kernel(const __grid_constant__ CUtensorMap tm_w, const ResidentArg
             __syncwarp();
             RES_TRACE(32 * s + 22 + 4 * (warp_idx == 11), t, lane == 0 && (warp_idx == 4 || warp_idx == 11));
             if (t + 1 < args.steps) {
-              // This warp's 32 words (32 chains x 32 units) go to every CTA that computes the next half-step: staged in
-              // local shared memory, then ONE 128-byte bulk copy per destination (one complete_tx on its barrier;
-              // per-lane st.async cost 256 barrier updates per CTA pair and half-step and serialised on the barrier).
-              // The staging slot alternates with the use count: the copy issued two uses ago has been consumed.
+              // The CTA's words of this half-step (128 chains x 2 words = 1 KB, laid out like the consumer's buffer) are
+              // staged in local shared memory by the eight epilogue warps, which meet on a named barrier; ONE warp then
+              // issues one 1 KB bulk copy per destination CTA (one complete_tx per copy on the destination's barrier for
+              // this source CTA).  (128-byte copies per warp: 64 instead of 8 copies per CTA and half-step, ~100 issued
+              // instructions per warp; per-lane st.async: 256 barrier updates per CTA pair and half-step.)
+              // The staging block alternates with the use count: the copies issued two uses ago have been consumed.
               const int par = (t + 1) & 1;
-              const uint32_t stg = smem_base + L.stage + (uint32_t)(((s * 2 + (int)(uses[s] & 1u)) * kResEpiWarps + (warp_idx - 4)) * 128);
-              st_shared_u32(stg + (uint32_t)lane * 4u, bits);
+              const uint32_t stg = smem_base + L.stage + (uint32_t)((s * 2 + (int)(uses[s] & 1u)) * 1024);
+              st_shared_u32(stg + (uint32_t)(cq * 512 + row_in_blk * 4), bits);
               fence_proxy_async_smem();
-              __syncwarp();
-              {
-                // one elected lane issues the copies to all destination CTAs back to back (per-lane issue compiles to a
-                // serialised loop of 8 instructions per copy: the operands must be moved to uniform registers lane by lane)
-                const uint32_t dst = bits_addr(s, par, 2 * j + cq, quarter * 32);
+              named_bar_sync(3, 32 * kResEpiWarps);
+              if (warp_idx == 4) {
+                const uint32_t dst = bits_addr(s, par, 2 * j, 0);
                 const uint32_t bar = bits_full(s, par, j);      // this CTA is K block j of its consumers
                 const int n_dst = dir ? args.n_tiles[0] : args.n_tiles[1];
                 if (elect_one_sync()) {
 #pragma unroll
                   for (int d = 0; d < kResMaxTiles; ++d)
-                    if (d < n_dst) dsmem_bulk_copy(mapa_u32(dst, (uint32_t)d), stg, 128u, mapa_u32(bar, (uint32_t)d));
+                    if (d < n_dst) dsmem_bulk_copy(mapa_u32(dst, (uint32_t)d), stg, 1024u, mapa_u32(bar, (uint32_t)d));
                 }
+                __syncwarp();
               }
-              __syncwarp();
               RES_TRACE(32 * s + 23 + 4 * (warp_idx == 11), t, lane == 0 && (warp_idx == 4 || warp_idx == 11));
             }
             ++uses[s];
